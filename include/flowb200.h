@@ -1,0 +1,158 @@
+/* flowb200 — C ABI of the B200-native discrete-optical-flow hot path.
+ *
+ * The reference (pfe-rs/lk-s-2022-estimacija-pokreta) has no FFI: its boundary is process CLI +
+ * .npy files + one importable module.  This header is the C boundary the
+ * drop-in scripts in this repository bind with ctypes; each entry point names the reference
+ * function (file:line under /root/reference) whose work it performs.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - images are row-major, index [y][x]; flow vectors are (dy, dx) = (rows, cols) as in the
+ *     reference (daisy i flann.py:173), packed on the device as one int32:
+ *         pvec = (uint16)dy | ((uint16)dx << 16)          (two's complement int16 halves);
+ *     an unused proposal slot is (-1,-1) = 0xFFFFFFFF with data cost 1000.0f, as the reference
+ *     fills them (daisy i flann.py:89-90);
+ *   - no global state, no allocation inside the per-stage calls: the caller owns all memory and
+ *     passes a workspace whose size the matching *_workspace_bytes() call returns;
+ *   - every call enqueues on `stream` and returns without synchronising; it returns 0 or a
+ *     negative FLOWB200_E* code (flowb200_error_string()).
+ */
+#ifndef FLOWB200_H
+#define FLOWB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* flowb200_stream_t;
+
+#define FLOWB200_DESC_DIM 68        /* DAISY(5,4,4,4): 17 regions x 4 bins (daisy i flann.py:66)   */
+#define FLOWB200_UNUSED_COST 1000.0f /* lcosts fill (daisy i flann.py:90)                           */
+
+enum {
+  FLOWB200_OK = 0,
+  FLOWB200_EINVAL = -1,      /* bad argument / unsupported parameter combination */
+  FLOWB200_EWORKSPACE = -2,  /* workspace too small                              */
+  FLOWB200_ECUDA = -3,       /* a CUDA runtime call failed (see flowb200_last_cuda_error) */
+  FLOWB200_EUNSUPPORTED = -4
+};
+
+/* BCD arithmetic (python bcd.py:101-257).
+ *   FP64_F32COST / FP64_F64COST: float64 dynamic programme with the reference's operation order,
+ *       bit-exact labels for arbitrary data costs (cost array float32 resp. float64);
+ *   INT32: int32 dynamic programme in units of 2^-cost_shift on integer data costs m
+ *       (lamda*lcost*2^S == m); bit-exact with the reference whenever lcost == 20*m/2^S. */
+enum { FLOWB200_BCD_FP64_F32COST = 0, FLOWB200_BCD_FP64_F64COST = 1, FLOWB200_BCD_INT32 = 2 };
+
+/* how the per-cell nearest-neighbour search is carried out (all give the exact answer) */
+enum { FLOWB200_KNN_EXACT_FP64 = 0,   /* brute force, float64 CUDA cores                              */
+       FLOWB200_KNN_TCGEN05 = 1 };    /* fp16 tcgen05 GEMM prefilter + float64 re-rank + certified fallback */
+
+typedef struct flowb200_params {
+  int32_t H, W;              /* pich, picw            daisy i flann.py:34-35 */
+  int32_t cellw, cellh;      /*                        :42-43                 */
+  int32_t cell_radius;       /* 2                      :167-168               */
+  int32_t k_cell;            /* 5 neighbours per cell  :171-172               */
+  int32_t n_gauss;           /* 25                     :207                   */
+  float sigma;               /* 8                      :208                   */
+  int32_t maxnprop;          /* 150                    :88                    */
+  float tphi;                /* 2.5                    :46                    */
+  int32_t tpsi;              /* 8                      :47                    */
+  double lamda;              /* 0.05                   :48                    */
+  int32_t cost_shift;        /* S of the INT32 BCD mode                      */
+  int32_t bcd_mode;          /* FLOWB200_BCD_*                                */
+  int32_t knn_mode;          /* FLOWB200_KNN_*                                */
+  float con_tresh;           /* 10   README.md:65                             */
+} flowb200_params;
+
+int flowb200_version(void);
+const char* flowb200_error_string(int code);
+const char* flowb200_last_cuda_error(void);
+
+/* ---- A2  izracunajDaisy  (daisy i flann.py:69-77; cv2.xfeatures2d.DAISY_create(5,4,4,4), :66) ---- */
+size_t flowb200_daisy_workspace_bytes(int H, int W);
+/* bgr: uint8 [H][W][3];  desc: float32 [H][W][68] */
+int flowb200_daisy(const uint8_t* bgr, int H, int W, float* desc, void* workspace, size_t workspace_bytes,
+                   flowb200_stream_t stream);
+
+/* ---- A3+A4  napraviCD2 + generisi  (daisy i flann.py:144-148, 157-189) ----
+ * Exact k_cell nearest neighbours (squared L2 in float64, ties -> lowest target index) of every source
+ * pixel in every target cell within +-cell_radius cells; writes the NN proposal slots in the reference's
+ * slot order, their truncated-L1 data costs, nprop, and bestlabels (first strict argmin, :181-184);
+ * slots >= nprop are filled (-1,-1) / 1000.
+ *   pvec int32 [H][W][K], lcost float32 [H][W][K], nprop int32 [H][W], labels int32 [H][W]
+ *   knn_idx (optional, may be NULL): int32 [H][W][(2r+1)^2][k_cell] target index inside the cell
+ *       (idx = row*cellw + col, :147-148), -1 for cells out of range; block order = slot order.
+ *   stats (optional): int32[4] device counters {uncertified (query,cell) pairs re-done exactly, ...}. */
+size_t flowb200_knn_workspace_bytes(const flowb200_params* p);
+int flowb200_knn_proposals(const float* desc_src, const float* desc_tgt, const flowb200_params* p,
+                           int32_t* pvec, float* lcost, int32_t* nprop, int32_t* labels, int32_t* knn_idx,
+                           int32_t* stats, void* workspace, size_t workspace_bytes, flowb200_stream_t stream);
+
+/* ---- A6  nasumicni  (daisy i flann.py:205-233), quirks Q4/Q6 reproduced ----
+ * draws: optional int16 [H][W][n_gauss][2] accepted in-bounds (tgy,tgx) samples to replay (parity mode);
+ * NULL -> Philox4x32-10 Gaussian draws from `seed` with the reference's rejection rules. */
+int flowb200_random_proposals(const float* desc_src, const float* desc_tgt, const flowb200_params* p,
+                              int32_t* pvec, float* lcost, int32_t* nprop, const int32_t* labels,
+                              const int16_t* draws, uint64_t seed, flowb200_stream_t stream);
+
+/* ---- A8  pakovanje  (daisy i flann.py:256-309): legacy packedksets export, small sizes only ----
+ * packed: uint8 [H][W][2][K*K/8+1], slot 0 = down neighbour, slot 1 = right; bits outside
+ * [:nprop[p], :nprop[q]] are zero. */
+int flowb200_ksets_pack(const int32_t* pvec, const int32_t* nprop, int H, int W, int K, int tpsi,
+                        uint8_t* packed, flowb200_stream_t stream);
+
+/* lamda*lcost -> integer units of 2^-S (rint), unused slots -> 0.  m: int32 [n] */
+int flowb200_quantise_costs(const float* lcost, int32_t* m, size_t n, double lamda, int shift,
+                            flowb200_stream_t stream);
+
+/* ---- A9-A11  bcd / ceoBCD  (python bcd.py:101-257, 261-284) ----
+ * Runs `sweeps` sweeps of the four phases (even columns down, even rows right-to-left, odd columns up,
+ * odd rows left-to-right) on `labels` in place.  cost: float32 / float64 / int32 [H][W][K] per bcd_mode.
+ * labels_per_sweep (optional): int32 [sweeps][H][W] snapshot after every sweep (what ceoBCD saves). */
+size_t flowb200_bcd_workspace_bytes(int H, int W, int K);
+int flowb200_bcd(const int32_t* pvec, const void* cost, const int32_t* nprop, int32_t* labels,
+                 int H, int W, int K, int bcd_mode, double lamda, int tpsi, int cost_shift, int sweeps,
+                 int32_t* labels_per_sweep, void* workspace, size_t workspace_bytes, flowb200_stream_t stream);
+
+/* ---- A5  vratiKonacniFlow (daisy i flann.py:192-197) + A12 FlowImage.ucitajFlow (postprocessing.py:7-17) ----
+ * flow_yx (optional): float64 [H][W][2] = (dy,dx);  uvv (optional): float32 [H][W][3] = (dx, dy, 1). */
+int flowb200_flow_from_labels(const int32_t* pvec, const int32_t* labels, int H, int W, int K,
+                              double* flow_yx, float* uvv, flowb200_stream_t stream);
+
+/* ---- A13/A14  consistencyCheck / fowardBackwardConsistency (postprocessing.py:79-117) ----
+ * flow1 (in place) and flow2: float32 [A][B][3] = (dx, dy, valid).  Quirk Q5 (dx added to the row index)
+ * is reproduced.  Only pixels a0<=a<a1, b0<=b<b1 are checked (whole image: 0,A,0,B). */
+int flowb200_consistency(float* flow1, const float* flow2, int A, int B, float tresh,
+                         int a0, int a1, int b0, int b1, flowb200_stream_t stream);
+
+/* ---- whole path, device resident: two DAISYs, per direction kNN + random proposals + `sweeps` BCD
+ *      sweeps, then the forward/backward check.  bgr0/bgr1: uint8 [H][W][3].
+ * out_fwd: float32 [H][W][3] checked forward field (sparse_field.npy layout); out_fwd_raw / out_bwd_raw
+ * (optional): unchecked (dx,dy,1) fields of both directions. directions: 1 = forward only (no check),
+ * 2 = forward + backward + check. */
+size_t flowb200_pair_workspace_bytes(const flowb200_params* p);
+int flowb200_flow_pair(const uint8_t* bgr0, const uint8_t* bgr1, const flowb200_params* p, int sweeps,
+                       int directions, uint64_t seed, float* out_fwd, float* out_fwd_raw, float* out_bwd_raw,
+                       void* workspace, size_t workspace_bytes, flowb200_stream_t stream);
+
+/* ---- host-buffer convenience context (what the drop-in scripts and the e2e benchmark call) ----
+ * Owns device workspace, pinned staging buffers and a stream on the current device. */
+typedef struct flowb200_ctx flowb200_ctx;
+flowb200_ctx* flowb200_ctx_create(const flowb200_params* p);
+void flowb200_ctx_destroy(flowb200_ctx* ctx);
+/* bgr0_host/bgr1_host: uint8 [H][W][3] host memory; out_fwd_host: float32 [H][W][3] host memory.
+ * Copies in, runs flowb200_flow_pair, copies out, synchronises. */
+int flowb200_ctx_flow_pair_host(flowb200_ctx* ctx, const uint8_t* bgr0_host, const uint8_t* bgr1_host,
+                                int sweeps, int directions, uint64_t seed, float* out_fwd_host);
+/* postprocessing.fowardBackwardConsistency on host arrays (flow1_host modified in place). */
+int flowb200_consistency_host(float* flow1_host, const float* flow2_host, int A, int B, float tresh,
+                              int a0, int a1, int b0, int b1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWB200_H */

@@ -1,0 +1,59 @@
+"""DAISY oracle: primitives pinned against the cv2 main-module calls daisy.cpp makes (CPU only)."""
+import numpy as np
+import pytest
+
+from helpers import pkg
+from oracle import daisy as od
+
+cv2 = pytest.importorskip("cv2")
+
+
+def _img(H=57, W=83, seed=4):
+    return pkg("synth").texture(H, W, seed)
+
+
+def test_gray_matches_cvtcolor():
+    img = _img()
+    assert np.array_equal(od.gray_u8(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+
+
+def test_kernels_match_getgaussiankernel():
+    sig = [0.5, np.sqrt(1.6 ** 2 - 0.25), 0.625, np.sqrt(1.25 ** 2 - 0.625 ** 2),
+           np.sqrt(1.875 ** 2 - 1.25 ** 2), np.sqrt(2.5 ** 2 - 1.875 ** 2)]
+    ks = [5, 7, 3, 5, 7, 9]
+    for s, k in zip(sig, ks):
+        ref = cv2.getGaussianKernel(k, s, cv2.CV_32F).ravel()
+        assert np.allclose(od.gaussian_kernel(k, s), ref, rtol=0, atol=1e-7)
+    assert [len(t) for t in od.blur_taps()] == [7, 3, 5, 7, 9]
+
+
+def test_blur_and_gradient_match_cv2():
+    g = od.gray_u8(_img()).astype(np.float32) / np.float32(255)
+    for k, s in ((5, 0.5), (7, 1.5199), (9, 1.6536)):
+        ref = cv2.GaussianBlur(g, (k, k), s, sigmaY=s, borderType=cv2.BORDER_REPLICATE)
+        assert np.abs(od.blur_sep(g, od.gaussian_kernel(k, s)) - ref).max() < 3e-7
+    dx, dy = od.central_gradient(g)
+    assert np.array_equal(dx, cv2.Sobel(g, cv2.CV_32F, 1, 0, ksize=1, scale=0.5, borderType=cv2.BORDER_REPLICATE))
+    assert np.array_equal(dy, cv2.Sobel(g, cv2.CV_32F, 0, 1, ksize=1, scale=0.5, borderType=cv2.BORDER_REPLICATE))
+
+
+def test_descriptor_shape_and_border_rules():
+    img = _img()
+    d = od.daisy(img)
+    H, W, _ = img.shape
+    assert d.shape == (H, W, 68) and d.dtype == np.float32
+    assert (d >= 0).all()
+    assert (d[:, W - 2:, 0:4] == 0).all() and (d[H - 2:, :, 0:4] == 0).all()     # mnx>=W-2 / mny>=H-2
+    assert (d[:, 0, 4 * (1 + 2):4 * (1 + 3)] == 0).all()                            # ring 0, angle pi: x-1.25 < 0
+    assert d[5:-5, 5:-5].min(axis=(0, 1)).max() >= 0 and d[10:-10, 10:-10].max() > 1e-3
+
+
+def test_true_match_is_nearest():
+    synth = pkg("synth")
+    img1 = synth.texture(64, 96, 2)
+    img2 = np.roll(img1, (3, -5), axis=(0, 1))
+    d1, d2 = od.daisy(img1), od.daisy(img2)
+    a = d1[20:40, 30:60]
+    b = d2[23:43, 25:55]
+    assert np.abs(a - b).sum(-1).max() < 1e-5
+    assert np.abs(a - d2[20:40, 30:60]).sum(-1).mean() > 0.05
