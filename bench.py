@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the flow hot path (BASELINE.json metric: flow Mpix/s & pairs/s, DAISY+kNN+BCD+consistency).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl flowb200|reference] [--workload NAME]
+
+One step = one synthetic image pair through the whole path: 2 x DAISY, per direction exact per-cell kNN
+proposals + random-neighbour proposals + `sweeps` BCD sweeps, then the forward/backward check.
+Workload (default) = BASELINE.json configs[1]: 1024x436, forward+backward+consistencyCheck(10), K=300,
+bcd_times=4.  With N GPUs every rank processes its own pair per step (pairs are independent, README.md:40):
+weak scaling, no data-path collective; value = N pairs / max-over-ranks time.
+
+value  : device-resident (images already in HBM), CUDA events, max over ranks.
+e2e    : the same through the host-buffer C ABI (flowb200_ctx_flow_pair_host): pinned H2D of both images,
+         D2H of the checked field, inside the timed region.
+roofline: the dominant stage, algorithmic bytes/FLOPs / its CUDA-event time measured here.
+cpu_baseline: the CPU oracle (oracle/, C + numpy, all host threads) on a bounded crop of the same workload.
+--impl reference: the CPU oracle alone, same metric/config (the reference itself is pure Python that
+         needs opencv-contrib + pyflann, absent offline; its unmodified source runs only on tiny crops).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "lk-s-2022-estimacija-pokreta_b200"
+
+WORKLOADS = {
+    # name: (H, W, K, sweeps, directions)
+    "1024x436_fwd_K150_bcd4": (436, 1024, 150, 4, 1),            # configs[0]
+    "1024x436_fwdbwd_K300_bcd4": (436, 1024, 300, 4, 2),         # configs[1]  (metric is quoted on this)
+    "1242x375_fwdbwd_K500_bcd8": (375, 1242, 500, 8, 2),         # configs[2]
+}
+DEFAULT_WORKLOAD = "1024x436_fwdbwd_K300_bcd4"
+METRIC = "flow Mpix/s (DAISY+kNN+BCD+consistency)"
+
+
+def mod(name):
+    return importlib.import_module(PKG + "." + name)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"], "tensor": d["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) >= 7 and r[3 + j].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_params(workload, knn_mode):
+    H, W, K, sweeps, directions = WORKLOADS[workload]
+    P = mod("params")
+    p = P.for_k(K, H=H, W=W, knn_mode=knn_mode)
+    return p, sweeps, directions
+
+
+def algorithmic_work(p, sweeps, directions):
+    """Per-step algorithmic bytes / FLOPs of every stage (DESIGN.md 'Measurement')."""
+    N = p.H * p.W
+    T = p.cellw * p.cellh
+    R = p.cell_radius
+    q = 0
+    for ci in range(p.ncellx):
+        bw = min(p.W, p.cellw * (ci + R + 1)) - max(0, p.cellw * (ci - R))
+        for cj in range(p.ncelly):
+            bh = min(p.H, p.cellh * (cj + R + 1)) - max(0, p.cellh * (cj - R))
+            q += bw * bh
+    K = p.maxnprop
+    return {
+        "daisy": ("hbm", 2 * N * (3 + 68 * 4)),
+        "knn": ("tensor", directions * 2 * 68 * q * T),
+        "random": ("hbm", directions * N * (2 * 272 + p.n_gauss * 16)),
+        "bcd": ("hbm", directions * sweeps * 2 * N * (K * 8 + 12)),
+        "consistency": ("hbm", (directions - 1) * N * 28 + directions * N * 16),
+    }
+
+
+def stage_breakdown(ops, lib, p, sweeps, directions, g0, g1, bcd_mode, reps=2):
+    """CUDA-event time of every stage, the same C-ABI calls flowb200_flow_pair makes, on torch's stream."""
+    import torch
+    acc = {k: 0.0 for k in ("daisy", "knn", "random", "bcd", "consistency")}
+
+    def timed(key, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        b.synchronize()
+        acc[key] += a.elapsed_time(b)
+        return r
+    for rep in range(reps + 1):
+        if rep == 1:
+            acc = {k: 0.0 for k in acc}          # first pass is warm-up
+        d = timed("daisy", lambda: (ops.daisy(g0), ops.daisy(g1)))
+        uv = []
+        for di in range(directions):
+            src, tgt = d[di], d[1 - di]
+            pv, lc, npr, lab = timed("knn", lambda: ops.knn_proposals(src, tgt, p))
+            timed("random", lambda: ops.random_proposals(src, tgt, p, pv, lc, npr, lab, seed=di))
+
+            def run_bcd():
+                cost = lc
+                if bcd_mode == lib.BCD_INT32:
+                    cost = ops.quantise_costs(lc, p.lamda, p.cost_shift)
+                ops.bcd(pv, cost, npr, lab, sweeps, mode=bcd_mode, lamda=p.lamda, tpsi=p.tpsi, cost_shift=p.cost_shift)
+            timed("bcd", run_bcd)
+            uv.append(timed("consistency", lambda: ops.flow_from_labels(pv, lab, want_yx=False)[1]))
+        if directions == 2:
+            timed("consistency", lambda: ops.consistency(uv[0], uv[1], p.con_tresh))
+    return {k: v / reps for k, v in acc.items()}
+
+
+def cpu_oracle_pipeline(img1, img2, op, sweeps, directions, con_tresh, seed=0):
+    """The whole path on the CPU oracle (numpy DAISY + C generisi/nasumicni/BCD/consistency)."""
+    from oracle import consistency as ocons, cport, daisy as od, proposals as oprop
+    d = (od.daisy(img1), od.daisy(img2))
+    flows = []
+    for di in range(directions):
+        a, b = d[di], d[1 - di]
+        P, L, N, B = cport.generisi(a, b, op)
+        P, L, N = cport.nasumicni(a, b, P, L, N, B, op, seed=seed + di)
+        lab = cport.ceo_bcd(P, L, N, B, sweeps, tpsi=op.tpsi, lamda=op.lamda)[-1]
+        flows.append(oprop.final_flow(P, lab))
+    if directions == 2:
+        return ocons.forward_backward_consistency(ocons.ucitaj_flow(flows[0]), ocons.ucitaj_flow(flows[1]), con_tresh)
+    return ocons.ucitaj_flow(flows[0])
+
+
+def cpu_sample(p, sweeps, directions, steps=1):
+    """Bounded sample of the workload for the CPU oracle: a crop of 5x3 cells (every pixel of the middle
+    column of cells sees the full 5-cell search width), same K / sweeps / directions."""
+    from oracle import cport
+    from oracle.proposals import Params
+    synth = mod("synth")
+    Hs, Ws = min(p.H, 3 * p.cellh), min(p.W, 5 * p.cellw)
+    op = Params(Hs, Ws, p.cellw, p.cellh, p.cell_radius, p.k_cell, p.n_gauss, p.sigma, p.maxnprop, p.tphi, p.tpsi,
+                p.lamda)
+    img1, img2, _, _ = synth.make_pair(Hs, Ws, 0)
+    cpu_oracle_pipeline(img1[:p.cellh * 1 + 20, :p.cellw + 20], img2[:p.cellh + 20, :p.cellw + 20],
+                        Params(p.cellh + 20, p.cellw + 20, p.cellw, p.cellh, p.cell_radius, p.k_cell, p.n_gauss,
+                               p.sigma, p.maxnprop, p.tphi, p.tpsi, p.lamda), 1, directions, p.con_tresh)   # warm-up
+    ts = []
+    for s in range(steps):
+        t0 = time.perf_counter()
+        cpu_oracle_pipeline(img1, img2, op, sweeps, directions, p.con_tresh, seed=s)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.mean(ts))
+    return {"value": Hs * Ws / 1e6 / t, "unit": "Mpix/s", "cores": cport.num_threads(), "kind": "port",
+            "sample": f"{Ws}x{Hs} crop (5x3 cells of {p.cellw}x{p.cellh}), K={p.maxnprop}, bcd_times={sweeps}, "
+                      f"{directions} direction(s), {t:.2f} s/step; C oracle with OpenMP + numpy DAISY",
+            "seconds_per_step": t}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    p, sweeps, directions = make_params(args.workload, 0)
+    steps = max(1, min(args.steps, 3))
+    r = cpu_sample(p, sweeps, directions, steps=steps)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Mpix/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": 1, "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "H": p.H, "W": p.W, "K": p.maxnprop, "bcd_times": sweeps,
+                       "directions": directions},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="flowb200", choices=["flowb200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--knn-mode", type=int, default=None)
+    ap.add_argument("--bcd-mode", default="int32", choices=["int32", "fp64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    lib, ops, synth = mod("_lib"), mod("ops"), mod("synth")
+    L = lib.load()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W_ = max(args.warmup, 3)
+    knn_mode = args.knn_mode if args.knn_mode is not None else mod("params").DEFAULT_KNN_MODE
+    p, sweeps, directions = make_params(args.workload, knn_mode)
+    bcd_mode = lib.BCD_INT32 if args.bcd_mode == "int32" else lib.BCD_FP64_F32COST
+    cp = ops.cparams(p, bcd_mode=bcd_mode)
+
+    # a few distinct synthetic pairs per rank, cycled (the per-step working set, ~GBs of proposals, is far
+    # larger than L2, so steps do not warm each other)
+    npairs = 2
+    pairs = [synth.make_pair(p.H, p.W, 10 * rank + i) for i in range(npairs)]
+    dev_pairs = [(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()) for a, b, _, _ in pairs]
+    ws = ops.pair_workspace(p, "cuda", bcd_mode)
+
+    def step(i):
+        g0, g1 = dev_pairs[i % npairs]
+        return ops.flow_pair(g0, g1, p, sweeps, directions, seed=i, bcd_mode=bcd_mode, workspace=ws)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W_):
+        out = step(i)
+    barrier()
+    launches0 = L.flowb200_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = step(W_ + i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (L.flowb200_launch_count() - launches0)
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    mpix = world * p.H * p.W / 1e6 / (ms_step / 1e3)
+
+    # ---- e2e: host buffers through the C-ABI context, H2D + D2H inside the timed region
+    ctx = L.flowb200_ctx_create(C.byref(cp))
+    if not ctx:
+        raise RuntimeError("flowb200_ctx_create failed: " + L.flowb200_last_cuda_error().decode())
+    host_out = np.empty((p.H, p.W, 3), dtype=np.float32)
+
+    def e2e_step(i):
+        a, b, _, _ = pairs[i % npairs]
+        lib.check(L.flowb200_ctx_flow_pair_host(ctx, a.ctypes.data, b.ctypes.data, sweeps, directions, i,
+                                                host_out.ctypes.data), "flowb200_ctx_flow_pair_host")
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(1 + i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_mpix = world * p.H * p.W / 1e6 / (float(t.item()) / args.steps)
+    L.flowb200_ctx_destroy(ctx)
+
+    if rank == 0:
+        pk = peaks()
+        work = algorithmic_work(p, sweeps, directions)
+        roof, stages = None, None
+        if not args.no_breakdown:
+            stages = stage_breakdown(ops, lib, p, sweeps, directions, dev_pairs[0][0], dev_pairs[0][1], bcd_mode)
+            dom = max(stages, key=stages.get)
+            kind, amount = work[dom]
+            secs = stages[dom] / 1e3
+            if kind == "hbm":
+                ach, peak, unit = amount / secs / 1e9, pk["hbm"], "GB/s"
+            else:
+                ach, peak, unit = amount / secs / 1e12, pk["tensor"], "TFLOP/s"
+            roof = {"kernel": dom, "bound": kind, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                    "traffic": None, "peak_source": pk["src"], "ms": stages[dom],
+                    "stage_ms": {k: round(v, 4) for k, v in stages.items()},
+                    "stage_frac_of_roofline": {
+                        k: round((work[k][1] / (v / 1e3) / (1e9 if work[k][0] == "hbm" else 1e12)) /
+                                 (pk["hbm"] if work[k][0] == "hbm" else pk["tensor"]), 5) if v > 0 else None
+                        for k, v in stages.items()}}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            r = cpu_sample(p, sweeps, directions)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {"metric": METRIC, "value": mpix, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": W_,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32" if bcd_mode == lib.BCD_INT32 else "f64", "data": "synthetic",
+                "pairs_per_s": world / (ms_step / 1e3),
+                "config": {"workload": args.workload, "H": p.H, "W": p.W, "K": p.maxnprop, "k_cell": p.k_cell,
+                           "n_gauss": p.n_gauss, "bcd_times": sweeps, "directions": directions,
+                           "knn_mode": knn_mode, "bcd_mode": args.bcd_mode, "parallelism": f"pairs x{world}",
+                           "l2": "per-step working set (proposals+costs, >1 GB) exceeds L2; 2 pairs cycled"},
+                "e2e": {"value": e2e_mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * p.H * p.W * 3,
+                        "d2h_bytes_per_step": p.H * p.W * 12},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

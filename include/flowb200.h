@@ -71,6 +71,8 @@ typedef struct flowb200_params {
 int flowb200_version(void);
 const char* flowb200_error_string(int code);
 const char* flowb200_last_cuda_error(void);
+/* number of kernel launches this process has enqueued through the library (diagnostics for bench.py) */
+long long flowb200_launch_count(void);
 
 /* ---- A2  izracunajDaisy  (daisy i flann.py:69-77; cv2.xfeatures2d.DAISY_create(5,4,4,4), :66) ---- */
 size_t flowb200_daisy_workspace_bytes(int H, int W);

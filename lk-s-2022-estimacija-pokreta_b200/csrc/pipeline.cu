@@ -1,0 +1,233 @@
+// Whole hot path, device resident: DAISY x2 -> per direction {kNN proposals, random proposals, BCD sweeps,
+// label->flow} -> forward/backward check.  This is what `daisy i flann.py` + `python bcd.py` (run once per
+// direction) + postprocessing.postProcessing compute between them, without the .npy round trips.
+// Also: error strings and the host-buffer context used by the drop-in scripts and the e2e benchmark.
+#include <atomic>
+#include <string>
+
+#include "common.cuh"
+
+namespace flowb200 {
+
+static thread_local std::string g_last_cuda_error;
+
+void set_cuda_error(cudaError_t e, const char* where) {
+  g_last_cuda_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " at " + where;
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct PairLayout {
+  size_t desc[2], daisy_ws, pvec[2], lcost[2], mcost[2], nprop[2], labels[2], uvv[2], bcd_ws[2], knn_ws[2], total;
+};
+
+static PairLayout pair_layout(const flowb200_params* p) {
+  PairLayout L{};
+  const size_t n = (size_t)p->H * p->W, K = (size_t)p->maxnprop;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes);
+    return o;
+  };
+  L.desc[0] = take(n * kDescDim * sizeof(float));
+  L.desc[1] = take(n * kDescDim * sizeof(float));
+  L.daisy_ws = take(flowb200_daisy_workspace_bytes(p->H, p->W));
+  for (int d = 0; d < 2; ++d) {
+    L.pvec[d] = take(n * K * sizeof(int32_t));
+    L.lcost[d] = take(n * K * sizeof(float));
+    L.mcost[d] = take(p->bcd_mode == FLOWB200_BCD_INT32 ? n * K * sizeof(int32_t) : 0);
+    L.nprop[d] = take(n * sizeof(int32_t));
+    L.labels[d] = take(n * sizeof(int32_t));
+    L.uvv[d] = take(n * 3 * sizeof(float));
+    L.bcd_ws[d] = take(flowb200_bcd_workspace_bytes(p->H, p->W, p->maxnprop));
+    L.knn_ws[d] = take(flowb200_knn_workspace_bytes(p));
+  }
+  L.total = off;
+  return L;
+}
+
+}  // namespace flowb200
+
+using namespace flowb200;
+
+extern "C" int flowb200_version(void) { return FLOWB200_VERSION; }
+
+extern "C" const char* flowb200_error_string(int code) {
+  switch (code) {
+    case FLOWB200_OK: return "ok";
+    case FLOWB200_EINVAL: return "invalid argument";
+    case FLOWB200_EWORKSPACE: return "workspace too small";
+    case FLOWB200_ECUDA: return "CUDA error";
+    case FLOWB200_EUNSUPPORTED: return "unsupported parameter combination";
+    default: return "unknown error";
+  }
+}
+
+extern "C" long long flowb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" const char* flowb200_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+
+extern "C" size_t flowb200_pair_workspace_bytes(const flowb200_params* p) {
+  if (!p || p->H <= 0 || p->W <= 0 || p->maxnprop <= 0) return 0;
+  return pair_layout(p).total;
+}
+
+static int run_direction(const flowb200_params* p, const PairLayout& L, char* ws, int d, int sweeps, uint64_t seed,
+                         cudaStream_t stream) {
+  const float* src = reinterpret_cast<const float*>(ws + L.desc[d]);
+  const float* tgt = reinterpret_cast<const float*>(ws + L.desc[1 - d]);
+  int32_t* pvec = reinterpret_cast<int32_t*>(ws + L.pvec[d]);
+  float* lcost = reinterpret_cast<float*>(ws + L.lcost[d]);
+  int32_t* nprop = reinterpret_cast<int32_t*>(ws + L.nprop[d]);
+  int32_t* labels = reinterpret_cast<int32_t*>(ws + L.labels[d]);
+  const size_t n = (size_t)p->H * p->W;
+  int rc = flowb200_knn_proposals(src, tgt, p, pvec, lcost, nprop, labels, nullptr, nullptr, ws + L.knn_ws[d],
+                                  flowb200_knn_workspace_bytes(p), stream);
+  if (rc) return rc;
+  rc = flowb200_random_proposals(src, tgt, p, pvec, lcost, nprop, labels, nullptr, seed + (uint64_t)d, stream);
+  if (rc) return rc;
+  const void* cost = lcost;
+  if (p->bcd_mode == FLOWB200_BCD_INT32) {
+    int32_t* m = reinterpret_cast<int32_t*>(ws + L.mcost[d]);
+    rc = flowb200_quantise_costs(lcost, m, n * p->maxnprop, p->lamda, p->cost_shift, stream);
+    if (rc) return rc;
+    cost = m;
+  } else if (p->bcd_mode != FLOWB200_BCD_FP64_F32COST) {
+    return FLOWB200_EINVAL;   // the pipeline produces float32 costs
+  }
+  rc = flowb200_bcd(pvec, cost, nprop, labels, p->H, p->W, p->maxnprop, p->bcd_mode, p->lamda, p->tpsi, p->cost_shift,
+                    sweeps, nullptr, ws + L.bcd_ws[d], flowb200_bcd_workspace_bytes(p->H, p->W, p->maxnprop), stream);
+  if (rc) return rc;
+  return flowb200_flow_from_labels(pvec, labels, p->H, p->W, p->maxnprop, nullptr,
+                                   reinterpret_cast<float*>(ws + L.uvv[d]), stream);
+}
+
+extern "C" int flowb200_flow_pair(const uint8_t* bgr0, const uint8_t* bgr1, const flowb200_params* p, int sweeps,
+                                  int directions, uint64_t seed, float* out_fwd, float* out_fwd_raw, float* out_bwd_raw,
+                                  void* workspace, size_t workspace_bytes, flowb200_stream_t stream) {
+  if (!bgr0 || !bgr1 || !p || !out_fwd || !workspace) return FLOWB200_EINVAL;
+  if (directions != 1 && directions != 2) return FLOWB200_EINVAL;
+  if (sweeps < 0) return FLOWB200_EINVAL;
+  const PairLayout L = pair_layout(p);
+  if (workspace_bytes < L.total) return FLOWB200_EWORKSPACE;
+  char* ws = static_cast<char*>(workspace);
+  const size_t n = (size_t)p->H * p->W;
+  const size_t dws = flowb200_daisy_workspace_bytes(p->H, p->W);
+  int rc = flowb200_daisy(bgr0, p->H, p->W, reinterpret_cast<float*>(ws + L.desc[0]), ws + L.daisy_ws, dws, stream);
+  if (rc) return rc;
+  rc = flowb200_daisy(bgr1, p->H, p->W, reinterpret_cast<float*>(ws + L.desc[1]), ws + L.daisy_ws, dws, stream);
+  if (rc) return rc;
+  for (int d = 0; d < directions; ++d) {
+    rc = run_direction(p, L, ws, d, sweeps, seed, stream);
+    if (rc) return rc;
+  }
+  const size_t fbytes = n * 3 * sizeof(float);
+  FB_CUDA_CHECK(cudaMemcpyAsync(out_fwd, ws + L.uvv[0], fbytes, cudaMemcpyDeviceToDevice, stream));
+  if (out_fwd_raw) FB_CUDA_CHECK(cudaMemcpyAsync(out_fwd_raw, ws + L.uvv[0], fbytes, cudaMemcpyDeviceToDevice, stream));
+  if (directions == 2) {
+    if (out_bwd_raw)
+      FB_CUDA_CHECK(cudaMemcpyAsync(out_bwd_raw, ws + L.uvv[1], fbytes, cudaMemcpyDeviceToDevice, stream));
+    rc = flowb200_consistency(out_fwd, reinterpret_cast<const float*>(ws + L.uvv[1]), p->H, p->W, p->con_tresh, 0,
+                              p->H, 0, p->W, stream);
+    if (rc) return rc;
+  }
+  return FLOWB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer context
+// ---------------------------------------------------------------------------------------------
+struct flowb200_ctx {
+  flowb200_params p;
+  cudaStream_t stream = nullptr;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  uint8_t* d_img[2] = {nullptr, nullptr};
+  float* d_out = nullptr;
+  uint8_t* h_img[2] = {nullptr, nullptr};   // pinned staging
+  float* h_out = nullptr;
+};
+
+extern "C" void flowb200_ctx_destroy(flowb200_ctx* c) {
+  if (!c) return;
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->ws);
+  cudaFree(c->d_img[0]);
+  cudaFree(c->d_img[1]);
+  cudaFree(c->d_out);
+  cudaFreeHost(c->h_img[0]);
+  cudaFreeHost(c->h_img[1]);
+  cudaFreeHost(c->h_out);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" flowb200_ctx* flowb200_ctx_create(const flowb200_params* p) {
+  if (!p || p->H <= 0 || p->W <= 0) return nullptr;
+  flowb200_ctx* c = new flowb200_ctx();
+  c->p = *p;
+  const size_t n = (size_t)p->H * p->W;
+  c->ws_bytes = flowb200_pair_workspace_bytes(p);
+  bool ok = c->ws_bytes > 0;
+  auto chk = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess) {
+      set_cuda_error(e, what);
+      ok = false;
+    }
+  };
+  if (ok) chk(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  if (ok) chk(cudaMalloc(&c->ws, c->ws_bytes), "cudaMalloc(workspace)");
+  for (int i = 0; i < 2 && ok; ++i) {
+    chk(cudaMalloc(reinterpret_cast<void**>(&c->d_img[i]), n * 3), "cudaMalloc(image)");
+    if (ok) chk(cudaHostAlloc(reinterpret_cast<void**>(&c->h_img[i]), n * 3, cudaHostAllocDefault), "cudaHostAlloc");
+  }
+  if (ok) chk(cudaMalloc(reinterpret_cast<void**>(&c->d_out), n * 3 * sizeof(float)), "cudaMalloc(out)");
+  if (ok) chk(cudaHostAlloc(reinterpret_cast<void**>(&c->h_out), n * 3 * sizeof(float), cudaHostAllocDefault), "cudaHostAlloc");
+  if (!ok) {
+    flowb200_ctx_destroy(c);
+    return nullptr;
+  }
+  return c;
+}
+
+extern "C" int flowb200_ctx_flow_pair_host(flowb200_ctx* c, const uint8_t* bgr0_host, const uint8_t* bgr1_host,
+                                           int sweeps, int directions, uint64_t seed, float* out_fwd_host) {
+  if (!c || !bgr0_host || !bgr1_host || !out_fwd_host) return FLOWB200_EINVAL;
+  const size_t n = (size_t)c->p.H * c->p.W;
+  memcpy(c->h_img[0], bgr0_host, n * 3);
+  memcpy(c->h_img[1], bgr1_host, n * 3);
+  FB_CUDA_CHECK(cudaMemcpyAsync(c->d_img[0], c->h_img[0], n * 3, cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA_CHECK(cudaMemcpyAsync(c->d_img[1], c->h_img[1], n * 3, cudaMemcpyHostToDevice, c->stream));
+  int rc = flowb200_flow_pair(c->d_img[0], c->d_img[1], &c->p, sweeps, directions, seed, c->d_out, nullptr, nullptr,
+                              c->ws, c->ws_bytes, c->stream);
+  if (rc) return rc;
+  FB_CUDA_CHECK(cudaMemcpyAsync(c->h_out, c->d_out, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  FB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  memcpy(out_fwd_host, c->h_out, n * 3 * sizeof(float));
+  return FLOWB200_OK;
+}
+
+extern "C" int flowb200_consistency_host(float* flow1_host, const float* flow2_host, int A, int B, float tresh, int a0,
+                                         int a1, int b0, int b1) {
+  if (!flow1_host || !flow2_host || A <= 0 || B <= 0) return FLOWB200_EINVAL;
+  const size_t bytes = (size_t)A * B * 3 * sizeof(float);
+  float *d1 = nullptr, *d2 = nullptr;
+  int rc = FLOWB200_OK;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d1), bytes);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d2), bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(d1, flow1_host, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d2, flow2_host, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc = flowb200_consistency(d1, d2, A, B, tresh, a0, a1, b0, b1, nullptr);
+    if (rc == FLOWB200_OK) e = cudaMemcpy(flow1_host, d1, bytes, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d1);
+  cudaFree(d2);
+  if (e != cudaSuccess) {
+    set_cuda_error(e, "flowb200_consistency_host");
+    return FLOWB200_ECUDA;
+  }
+  return rc;
+}

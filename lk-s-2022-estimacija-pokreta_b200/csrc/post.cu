@@ -1,0 +1,86 @@
+// Label -> flow gather and the forward/backward consistency check.
+//   flow_from_labels : vratiKonacniFlow (daisy i flann.py:192-197 / python bcd.py:90-95) fused with
+//                      FlowImage.ucitajFlow's (dx, dy, valid=1) float32 layout (postprocessing.py:7-17)
+//   consistency      : consistencyCheck / fowardBackwardConsistency (postprocessing.py:79-117)
+// Both are HBM-bound streaming kernels: 28 B/pixel algorithmic.
+#include "common.cuh"
+
+namespace flowb200 {
+
+__global__ void flow_from_labels_kernel(const int32_t* __restrict__ pvec, const int32_t* __restrict__ labels,
+                                        int n_pix, int K, double* __restrict__ flow_yx, float* __restrict__ uvv) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pix) return;
+  int32_t v = pvec[(size_t)i * K + labels[i]];
+  int dy = vec_dy(v), dx = vec_dx(v);
+  if (flow_yx) {
+    flow_yx[2 * (size_t)i] = (double)dy;
+    flow_yx[2 * (size_t)i + 1] = (double)dx;
+  }
+  if (uvv) {
+    uvv[3 * (size_t)i] = (float)dx;
+    uvv[3 * (size_t)i + 1] = (float)dy;
+    uvv[3 * (size_t)i + 2] = 1.0f;
+  }
+}
+
+// One thread per checked pixel (a, b) = (row, col) of flow1.  float32 arithmetic with explicit
+// round-to-nearest ops so that nothing is contracted into an FMA: the reference evaluates
+// du*du and dv*dv as separately rounded numpy float32 products (postprocessing.py:102-104).
+// Quirk Q5: channel 0 (dx) is added to the row index and tested against shape[0]; channel 1 (dy)
+// to the column index (postprocessing.py:80, 87-90).
+__global__ void consistency_kernel(float* __restrict__ f1, const float* __restrict__ f2, int A, int B,
+                                   float tresh, int a0, int a1, int b0, int b1) {
+  int nb = b1 - b0;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (a1 - a0) * nb) return;
+  int a = a0 + t / nb, b = b0 + t % nb;
+  size_t o = 3 * ((size_t)a * B + b);
+  float u = f1[o], v = f1[o + 1], val = f1[o + 2];
+  if (!(val > 0.5f)) return;
+  int a2 = (int)__fadd_rn(u, (float)a);   // int() truncates toward zero
+  int b2 = (int)__fadd_rn(v, (float)b);
+  bool bad = (a2 < 0 || b2 < 0 || a2 >= A || b2 >= B);
+  if (!bad) {
+    size_t o2 = 3 * ((size_t)a2 * B + b2);
+    float u2 = f2[o2], v2 = f2[o2 + 1], val2 = f2[o2 + 2];
+    if (!(val2 > 0.5f)) {
+      bad = true;
+    } else {
+      float du = __fadd_rn(u, u2), dv = __fadd_rn(v, v2);
+      float err = __fsqrt_rn(__fadd_rn(__fmul_rn(dv, dv), __fmul_rn(du, du)));
+      bad = err > tresh;
+    }
+  }
+  if (bad) {
+    f1[o] = 0.f;
+    f1[o + 1] = 0.f;
+    f1[o + 2] = 0.f;
+  }
+}
+
+}  // namespace flowb200
+
+using namespace flowb200;
+
+extern "C" int flowb200_flow_from_labels(const int32_t* pvec, const int32_t* labels, int H, int W, int K,
+                                         double* flow_yx, float* uvv, flowb200_stream_t stream) {
+  if (!pvec || !labels || H <= 0 || W <= 0 || K <= 0) return FLOWB200_EINVAL;
+  int n = H * W;
+  flow_from_labels_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pvec, labels, n, K, flow_yx, uvv);
+  FB_LAUNCH_CHECK();
+  return FLOWB200_OK;
+}
+
+extern "C" int flowb200_consistency(float* flow1, const float* flow2, int A, int B, float tresh, int a0, int a1,
+                                    int b0, int b1, flowb200_stream_t stream) {
+  if (!flow1 || !flow2 || A <= 0 || B <= 0) return FLOWB200_EINVAL;
+  if (a0 < 0 || b0 < 0 || a1 > A || b1 > B || a0 > a1 || b0 > b1) return FLOWB200_EINVAL;
+  // In place on flow1 while gathering flow2: when both alias, behaviour would be order dependent.
+  if (flow1 == flow2) return FLOWB200_EINVAL;
+  int n = (a1 - a0) * (b1 - b0);
+  if (n == 0) return FLOWB200_OK;
+  consistency_kernel<<<(n + 255) / 256, 256, 0, stream>>>(flow1, flow2, A, B, tresh, a0, a1, b0, b1);
+  FB_LAUNCH_CHECK();
+  return FLOWB200_OK;
+}

@@ -9,6 +9,9 @@ neighbours per cell and the number of Gaussian-sampled neighbour proposals grow,
 from dataclasses import dataclass, replace
 
 
+DEFAULT_KNN_MODE = 0          # FLOWB200_KNN_EXACT_FP64 until the tcgen05 prefilter is the default
+
+
 @dataclass(frozen=True)
 class FlowParams:
     H: int = 375                 # pich   (daisy i flann.py:35)
@@ -25,6 +28,7 @@ class FlowParams:
     lamda: float = 0.05          # :48
     con_tresh: float = 10.0      # README.md:65
     cost_shift: int = 12         # S: int32 BCD works in units of 2^-S (costs quantised to 20*m/2^S)
+    knn_mode: int = 0            # FLOWB200_KNN_* (0 = float64 CUDA cores, 1 = tcgen05 prefilter + exact re-rank)
 
     @property
     def ncellx(self):

@@ -1,0 +1,274 @@
+"""CUDA path vs the oracle and the golden fixtures (outputs of the reference's own source).  GPU only.
+
+Everything goes through the C ABI (libflowb200.so) via the package's ctypes layer.  Bars:
+bit-exact for labels, proposals, nprop, K-set bits, kNN indices, the consistency field and the
+float32 data costs; DAISY within 1e-4 relative to the per-descriptor maximum (north star).
+"""
+import numpy as np
+import pytest
+
+from helpers import load_case, load_npz, oracle_params, pkg
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+KNN_MODES = [0]       # 1 (tcgen05 prefilter) is added when that kernel lands
+DAISY_RTOL = 1e-4      # BASELINE.json north_star: "DAISY must agree within 1e-4 relative"
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def flow_params(meta, **kw):
+    H, W, cw, ch = (int(v) for v in meta[:4])
+    return pkg("params").FlowParams(H=H, W=W, cellw=cw, cellh=ch, **kw)
+
+
+# ---------------------------------------------------------------- consistency (A12-A14)
+@pytest.mark.parametrize("case", ["const", "randint", "real"])
+def test_consistency_golden(case):
+    from oracle import consistency as ocons
+    ops = pkg("ops")
+    z = load_npz("consistency")
+    f1 = dev(ocons.ucitaj_flow(z[case + "_fwd"]))
+    f2 = dev(ocons.ucitaj_flow(z[case + "_bwd"]))
+    ops.consistency(f1, f2, float(z[case + "_thr"]))
+    assert np.array_equal(f1.cpu().numpy(), z[case + "_out"])
+
+
+def test_consistency_random_float_flows():
+    from oracle import consistency as ocons
+    ops = pkg("ops")
+    rng = np.random.default_rng(3)
+    A, B = 97, 131
+    f1 = np.concatenate([rng.normal(0, 9, (A, B, 2)), (rng.random((A, B, 1)) > 0.1)], -1).astype(np.float32)
+    f2 = np.concatenate([-f1[..., :2] + rng.normal(0, 4, (A, B, 2)), (rng.random((A, B, 1)) > 0.1)], -1).astype(np.float32)
+    want = ocons.forward_backward_consistency(f1, f2, 7.5)
+    g1 = dev(f1)
+    ops.consistency(g1, dev(f2), 7.5)
+    assert np.array_equal(g1.cpu().numpy(), want)
+
+
+def test_consistency_empty_region_and_alias():
+    ops, lib = pkg("ops"), pkg("_lib")
+    f = torch.zeros((4, 5, 3), dtype=torch.float32, device="cuda")
+    ops.consistency(f, torch.zeros_like(f), 1.0, region=(2, 2, 0, 5))      # empty: no-op
+    with pytest.raises(lib.FlowB200Error):
+        ops.consistency(f, f, 1.0)
+
+
+# ---------------------------------------------------------------- DAISY (A2)
+@pytest.mark.parametrize("shape,seed", [((57, 83), 4), ((40, 48), 1), ((131, 200), 9)])
+def test_daisy_vs_oracle(shape, seed):
+    from oracle import daisy as od
+    ops = pkg("ops")
+    img = pkg("synth").texture(shape[0], shape[1], seed)
+    want = od.daisy(img)
+    got = ops.daisy(dev(img)).cpu().numpy()
+    scale = np.abs(want).max(axis=-1, keepdims=True) + 1e-12
+    rel = np.abs(got - want) / scale
+    assert rel.max() <= DAISY_RTOL, rel.max()
+    assert ((want == 0) == (got == 0)).all()          # zeroed border petals are exactly zero
+
+
+def test_daisy_golden_descriptors():
+    ops = pkg("ops")
+    z = load_npz("pair_a")
+    for img, want in ((z["img1"], z["desc1"]), (z["img2"], z["desc2"])):
+        got = ops.daisy(dev(img)).cpu().numpy()
+        scale = np.abs(want).max(axis=-1, keepdims=True) + 1e-12
+        assert (np.abs(got - want) / scale).max() <= DAISY_RTOL
+
+
+# ---------------------------------------------------------------- proposals (A3-A8)
+def _stage1_gpu(z, b, p, knn_mode=0):
+    ops, ioc = pkg("ops"), pkg("io_contract")
+    d1, d2 = (z["desc1"], z["desc2"]) if b == 0 else (z["desc2"], z["desc1"])
+    g1, g2 = dev(d1), dev(d2)
+    pvec, lcost, nprop, labels, idx, stats = ops.knn_proposals(g1, g2, p, want_idx=True, knn_mode=knn_mode)
+    out = {"labels00": labels.cpu().numpy().astype(np.int64),
+           "flow00": ops.flow_from_labels(pvec, labels)[0].cpu().numpy(),
+           "idx": idx.cpu().numpy(), "stats": stats.cpu().numpy()}
+    ops.random_proposals(g1, g2, p, pvec, lcost, nprop, labels, draws=dev(z[f"b{b}_draws"], torch.int16))
+    out.update(proposals=ioc.unpack_proposals(pvec.cpu().numpy()), lcosts=lcost.cpu().numpy().astype(np.float64),
+               nprop=nprop.cpu().numpy().astype(np.int64), pvec=pvec, nprop_dev=nprop)
+    return out
+
+
+@pytest.mark.parametrize("knn_mode", KNN_MODES)
+@pytest.mark.parametrize("name,dirs", [("pair_a", (0, 1)), ("pair_b", (0,))])
+def test_stage1_golden(name, dirs, knn_mode):
+    """generisi + nasumicni (replayed draws) + pakovanje against the reference's own outputs."""
+    from oracle import proposals as oprop
+    ops = pkg("ops")
+    z = load_case(name)
+    p = flow_params(z["meta"])
+    op = oracle_params(z["meta"])
+    for b in dirs:
+        r = _stage1_gpu(z, b, p, knn_mode)
+        assert np.array_equal(r["labels00"], z[f"b{b}_labels00"])
+        assert np.array_equal(r["flow00"], z[f"b{b}_flow00"])
+        assert np.array_equal(r["nprop"], z[f"b{b}_nprop"])
+        assert np.array_equal(r["proposals"], z[f"b{b}_proposals"])
+        assert np.array_equal(r["lcosts"], z[f"b{b}_lcosts"])
+        pk = ops.ksets_pack(r["pvec"], r["nprop_dev"]).cpu().numpy()
+        assert oprop.ksets_masked_equal(pk, z[f"b{b}_packedksets"], r["nprop"], op)
+
+
+@pytest.mark.parametrize("knn_mode", KNN_MODES)
+@pytest.mark.parametrize("k_cell", [5, 10])
+def test_knn_indices_bit_exact(knn_mode, k_cell):
+    """kNN indices against exact float64 brute force on the CPU (lowest-index ties), incl. duplicates."""
+    from oracle import proposals as oprop
+    ops = pkg("ops")
+    rng = np.random.default_rng(11)
+    H, W, cw, ch = 61, 90, 16, 12
+    img1, img2, _, _ = pkg("synth").make_pair(H, W, 5, max_dx=5, max_dy=3, n_rect=2)
+    from oracle import daisy as od
+    d1, d2 = od.daisy(img1), od.daisy(img2)
+    d2[10:14, 20:30] = d2[30:34, 40:50]          # exact duplicate targets -> ties inside / across cells
+    d2[5, 5:9] = d2[5, 4]
+    p = pkg("params").FlowParams(H=H, W=W, cellw=cw, cellh=ch, k_cell=k_cell, n_gauss=0,
+                                 maxnprop=25 * k_cell)
+    op = oprop.Params(H, W, cw, ch, k_cell=k_cell, n_gauss=0, maxnprop=25 * k_cell)
+    pvec, lcost, nprop, labels, idx, stats = ops.knn_proposals(dev(d1), dev(d2), p, want_idx=True, knn_mode=knn_mode)
+    idx = idx.cpu().numpy()
+    cd2 = oprop.cell_descriptors(d2, op)
+    R = p.cell_radius
+    ys = rng.integers(0, H, 40)
+    xs = rng.integers(0, W, 40)
+    for y, x in list(zip(ys, xs)) + [(0, 0), (H - 1, W - 1), (H - 1, 0), (0, W - 1)]:
+        cis = [c for c in range(op.ncellx) if cw * (c - R) <= x < cw * (c + R + 1)]
+        cjs = [c for c in range(op.ncelly) if ch * (c - R) <= y < ch * (c + R + 1)]
+        blk = 0
+        for ci in cis:
+            for cj in cjs:
+                want = oprop.knn_exact(d1[y, x][None], cd2[ci + cj * op.ncellx], k_cell)[0]
+                assert np.array_equal(idx[y, x, blk], want), (y, x, ci, cj)
+                blk += 1
+        assert (idx[y, x, blk:] == -1).all()
+        assert int(nprop[y, x]) == blk * k_cell
+    P, L, N, B = oprop.generisi(d1, d2, op)
+    ioc = pkg("io_contract")
+    assert np.array_equal(ioc.unpack_proposals(pvec.cpu().numpy()), P)
+    assert np.array_equal(lcost.cpu().numpy().astype(np.float64), L)
+    assert np.array_equal(labels.cpu().numpy(), B)
+
+
+def test_random_proposals_philox_statistics():
+    """Seeded Philox draws: same acceptance rules, so the kept-count distribution must look like the
+    reference's (about half of the 25 draws survive quirk Q4); reproducible for a fixed seed."""
+    ops = pkg("ops")
+    z = load_case("pair_a")
+    p = flow_params(z["meta"])
+    g1, g2 = dev(z["desc1"]), dev(z["desc2"])
+    runs = []
+    for seed in (7, 7, 8):
+        pvec, lcost, nprop, labels = ops.knn_proposals(g1, g2, p)
+        nn = nprop.clone()
+        ops.random_proposals(g1, g2, p, pvec, lcost, nprop, labels, seed=seed)
+        runs.append(((nprop - nn).cpu().numpy(), pvec.cpu().numpy()))
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    assert not np.array_equal(runs[0][1], runs[2][1])
+    kept = runs[0][0]
+    assert kept.min() >= 0 and kept.max() <= 25
+    # reference kept-count on this case (from the golden nprop): NN count is a multiple of 5 per pixel
+    from oracle import proposals as oprop
+    op = oracle_params(z["meta"])
+    _, _, N0, _ = oprop.generisi(z["desc1"], z["desc2"], op)
+    kept_ref = z["b0_nprop"] - N0
+    assert abs(kept.mean() - kept_ref.mean()) < 1.5, (kept.mean(), kept_ref.mean())
+
+
+# ---------------------------------------------------------------- BCD (A9-A11)
+@pytest.mark.parametrize("name,dirs", [("pair_a", (0, 1)), ("pair_b", (0,))])
+def test_bcd_fp64_golden(name, dirs):
+    """float64 mode on the reference's float32-representable costs: labels equal after every sweep."""
+    ops, ioc, lib = pkg("ops"), pkg("io_contract"), pkg("_lib")
+    z = load_case(name)
+    sweeps = int(z["meta"][5])
+    for b in dirs:
+        pvec = dev(ioc.pack_proposals(z[f"b{b}_proposals"]))
+        nprop = dev(z[f"b{b}_nprop"], torch.int32)
+        for mode, cost in ((lib.BCD_FP64_F32COST, dev(z[f"b{b}_lcosts"], torch.float32)),
+                           (lib.BCD_FP64_F64COST, dev(z[f"b{b}_lcosts"], torch.float64))):
+            labels = dev(z[f"b{b}_labels00"], torch.int32)
+            snaps = ops.bcd(pvec, cost, nprop, labels, sweeps, mode=mode, per_sweep=True).cpu().numpy()
+            for w in range(sweeps):
+                assert np.array_equal(snaps[w], z[f"b{b}_labels{w + 1:02d}"]), (b, mode, w)
+            assert np.array_equal(labels.cpu().numpy(), snaps[-1])
+            yx, uvv = ops.flow_from_labels(pvec, labels)
+            assert np.array_equal(yx.cpu().numpy(), z[f"b{b}_flow{sweeps:02d}"])
+
+
+def test_bcd_int32_golden():
+    """int32 mode on costs 20*m/2^12 against the unmodified reference's labels (bcd_q12 fixture)."""
+    ops, ioc, lib = pkg("ops"), pkg("io_contract"), pkg("_lib")
+    z = load_npz("bcd_q12")
+    sweeps, shift = int(z["meta"][5]), int(z["meta"][6])
+    pvec = dev(ioc.pack_proposals(z["proposals"]))
+    labels = dev(z["labels00"], torch.int32)
+    snaps = ops.bcd(pvec, dev(z["m"], torch.int32), dev(z["nprop"], torch.int32), labels, sweeps,
+                    mode=lib.BCD_INT32, cost_shift=shift, per_sweep=True).cpu().numpy()
+    for w in range(sweeps):
+        assert np.array_equal(snaps[w], z[f"labels{w + 1:02d}"]), w
+
+
+@pytest.mark.parametrize("H,W,K", [(37, 41, 150), (36, 64, 300), (48, 40, 500), (1, 40, 60), (40, 1, 60), (2, 2, 33)])
+def test_bcd_vs_oracle_random(H, W, K):
+    """Random proposal sets incl. degenerate shapes, ragged nprop, heavy ties (int costs), K up to 500."""
+    from oracle import bcd as obcd
+    ops, ioc, lib = pkg("ops"), pkg("io_contract"), pkg("_lib")
+    rng = np.random.default_rng(H * 1000 + W + K)
+    prop = rng.integers(-12, 13, (H, W, K, 2)).astype(np.int64)
+    nprop = rng.integers(max(1, K // 3), K + 1, (H, W)).astype(np.int64)
+    m = rng.integers(0, 513, (H, W, K)).astype(np.int64)
+    lab0 = (rng.integers(0, 1 << 30, (H, W)) % nprop).astype(np.int64)
+    lq = 20.0 * m / 4096.0
+    want = obcd.ceo_bcd(prop, lq, nprop, lab0, 2)
+    pvec = dev(ioc.pack_proposals(prop))
+    for mode, cost, kw in ((lib.BCD_INT32, dev(m, torch.int32), dict(cost_shift=12)),
+                           (lib.BCD_FP64_F64COST, dev(lq, torch.float64), {})):
+        labels = dev(lab0, torch.int32)
+        snaps = ops.bcd(pvec, cost, dev(nprop, torch.int32), labels, 2, mode=mode, per_sweep=True, **kw).cpu().numpy()
+        assert np.array_equal(snaps[0], want[0]) and np.array_equal(snaps[1], want[1]), mode
+
+
+def test_quantise_costs():
+    ops = pkg("ops")
+    rng = np.random.default_rng(0)
+    c = rng.uniform(0, 2.5, (9, 11, 20)).astype(np.float32)
+    c[..., 15:] = 1000.0
+    m = ops.quantise_costs(dev(c), 0.05, 12).cpu().numpy()
+    want = np.where(c == 1000.0, 0, np.rint(0.05 * c.astype(np.float64) * 4096.0)).astype(np.int32)
+    assert np.array_equal(m, want)
+
+
+# ---------------------------------------------------------------- whole path
+def test_pipeline_matches_stagewise_and_oracle():
+    """flow_pair (device resident) == the stages called one by one; EPE vs the oracle pipeline <= 0.01 px."""
+    from oracle import bcd as obcd, consistency as ocons, daisy as od, epe as oepe, proposals as oprop
+    ops, synth = pkg("ops"), pkg("synth")
+    H, W, cw, ch = 48, 64, 16, 12
+    img1, img2, fwd, bwd = synth.make_pair(H, W, 2, max_dx=6, max_dy=4, n_rect=2)
+    p = pkg("params").FlowParams(H=H, W=W, cellw=cw, cellh=ch, n_gauss=0, maxnprop=125)
+    out, raw_f, raw_b = ops.flow_pair(dev(img1), dev(img2), p, sweeps=2, directions=2, want_raw=True)
+    # oracle pipeline on the oracle's own descriptors, no random proposals (n_gauss = 0: deterministic)
+    op = oprop.Params(H, W, cw, ch, n_gauss=0, maxnprop=125)
+    d1, d2 = od.daisy(img1), od.daisy(img2)
+    flows = []
+    for a, b in ((d1, d2), (d2, d1)):
+        P, L, N, B = oprop.generisi(a, b, op)
+        lab = obcd.ceo_bcd(P, L, N, B, 2)[-1]
+        flows.append(oprop.final_flow(P, lab))
+    want = ocons.post_processing(flows[0], flows[1], p.con_tresh)
+    gt = synth.gt_uvv(fwd)
+    e_got = oepe.error_image(out.cpu().numpy(), gt)
+    e_want = oepe.error_image(want, gt)
+    assert abs(e_got[0] - e_want[0]) <= 0.01, (e_got, e_want)       # north star: EPE within 0.01 px
+    assert np.array_equal(raw_f.cpu().numpy(), ocons.ucitaj_flow(flows[0]))
+    assert np.array_equal(out.cpu().numpy(), want)

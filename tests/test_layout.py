@@ -1,0 +1,105 @@
+"""Boundary and layout rules that need no GPU: the C-ABI library loads and exports every symbol the header
+declares; the product package never touches oracle/; host-side contract helpers round-trip."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_DIR = os.path.join(ROOT, "lk-s-2022-estimacija-pokreta_b200")
+
+
+def header_symbols():
+    with open(os.path.join(ROOT, "include", "flowb200.h")) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(flowb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = pkg("_lib")
+    if not os.path.isfile(lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    L = lib.load()
+    names = header_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/flowb200.h but not exported"
+        assert n in lib.SYMBOLS, f"{n} has no ctypes prototype in _lib.SYMBOLS"
+    assert set(lib.SYMBOLS) == set(names)
+    assert L.flowb200_version() >= 100
+    assert L.flowb200_error_string(-2) == b"workspace too small"
+
+
+def test_workspace_queries_without_gpu():
+    import ctypes as C
+    lib, ops, params = pkg("_lib"), pkg("ops"), pkg("params")
+    L = lib.load()
+    p = params.for_k(300, H=436, W=1024)
+    cp = ops.cparams(p, bcd_mode=lib.BCD_INT32)
+    n = L.flowb200_pair_workspace_bytes(C.byref(cp))
+    assert 1 << 30 < n < 40 << 30
+    assert L.flowb200_daisy_workspace_bytes(0, 5) == 0
+    assert L.flowb200_bcd_workspace_bytes(436, 1024, 300) > 0
+
+
+def test_ops_refuse_cpu_tensors():
+    torch = pytest.importorskip("torch")
+    lib, ops = pkg("_lib"), pkg("ops")
+    with pytest.raises(lib.FlowB200Error):
+        ops.consistency(torch.zeros(2, 2, 3), torch.zeros(2, 2, 3), 1.0)
+
+
+def test_product_never_imports_oracle():
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle/|cport|ref_harness", re.M)
+    for dirpath, _, files in os.walk(PKG_DIR):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                with open(os.path.join(dirpath, fn), errors="ignore") as f:
+                    src = f.read()
+                # comments may mention oracle/ files as documentation; imports and paths in code may not
+                code = "\n".join(l for l in src.splitlines() if not l.lstrip().startswith(("//", "#", "*", "/*")))
+                assert not pat.search(code), f"{fn} references the oracle"
+    for script in ("daisy i flann.py", "bcd.py", "python bcd.py", "postprocessing.py"):
+        path = os.path.join(ROOT, script)
+        if os.path.isfile(path):
+            with open(path) as f:
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", f.read(), re.M), script
+
+
+def test_proposal_packing_round_trip():
+    ioc = pkg("io_contract")
+    rng = np.random.default_rng(0)
+    P = rng.integers(-300, 301, (5, 7, 11, 2)).astype(np.int64)
+    P[0, 0, 5:] = -1
+    v = ioc.pack_proposals(P)
+    assert v.dtype == np.int32 and (v[0, 0, 5:] == -1).all()
+    assert np.array_equal(ioc.unpack_proposals(v), P)
+    with pytest.raises(ValueError):
+        ioc.pack_proposals(np.array([[[[40000, 0]]]]))
+
+
+def test_quantised_cost_detection():
+    ioc = pkg("io_contract")
+    m = np.arange(0, 513, dtype=np.int64).reshape(1, 1, -1)
+    lq = 20.0 * m / 4096.0
+    got = ioc.quantised_m(lq, 0.05, 12)
+    assert got is not None and np.array_equal(got, m)
+    lq2 = lq.copy()
+    lq2[0, 0, 3] = 0.123456789
+    assert ioc.quantised_m(lq2, 0.05, 12) is None
+    lq[0, 0, 7] = 1000.0
+    assert ioc.quantised_m(lq, 0.05, 12)[0, 0, 7] == 0
+
+
+def test_file_names_match_reference_contract():
+    ioc = pkg("io_contract")
+    assert ioc.flow_file(6, 0, 0) == "Gotova flow slika 106 backward=0 posle 00 BCD.npy"
+    assert ioc.labels_file(12, 1, 4) == "Bestlabels fajl slike 112 backward=1 posle 04 BCD.npy"
+    assert ioc.stage1_file(6, 0, "nprop") == "Daisy output slike 106 backward=0 nprop.npy"
+    a, b = ioc.image_paths(6, 1)
+    assert a.endswith("image_2/000106_11.png") and b.endswith("image_2/000106_10.png")
