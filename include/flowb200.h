@@ -94,6 +94,14 @@ int flowb200_knn_proposals(const float* desc_src, const float* desc_tgt, const f
                            int32_t* pvec, float* lcost, int32_t* nprop, int32_t* labels, int32_t* knn_idx,
                            int32_t* stats, void* workspace, size_t workspace_bytes, flowb200_stream_t stream);
 
+/* diagnostics of the FLOWB200_KNN_TCGEN05 path: geom_out_host (host int32[8]) = {Tpad, stride s of the target
+ * permutation pos -> idx = pos*s mod T, tiles_x, tiles_y, n_items, tile_w, tile_h, max candidates};
+ * scores (optional, device float32 [n_items][128][Tpad]) = raw tensor-core ranking scores of every
+ * (cell, 16x8 query tile) work item, item = cell*tiles_x*tiles_y + tile.  Synchronises. */
+int flowb200_knn_debug_scores(const float* desc_src, const float* desc_tgt, const flowb200_params* p, float* scores,
+                              int32_t* geom_out_host, void* workspace, size_t workspace_bytes,
+                              flowb200_stream_t stream);
+
 /* ---- A6  nasumicni  (daisy i flann.py:205-233), quirks Q4/Q6 reproduced ----
  * draws: optional int16 [H][W][n_gauss][2] accepted in-bounds (tgy,tgx) samples to replay (parity mode);
  * NULL -> Philox4x32-10 Gaussian draws from `seed` with the reference's rejection rules. */

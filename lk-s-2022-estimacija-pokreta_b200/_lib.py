@@ -41,6 +41,7 @@ SYMBOLS = {
     "flowb200_daisy": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     "flowb200_knn_workspace_bytes": (C.c_size_t, [_PP]),
     "flowb200_knn_proposals": (C.c_int, [_P, _P, _PP, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "flowb200_knn_debug_scores": (C.c_int, [_P, _P, _PP, _P, _P, _P, C.c_size_t, _P]),
     "flowb200_random_proposals": (C.c_int, [_P, _P, _PP, _P, _P, _P, _P, _P, C.c_uint64, _P]),
     "flowb200_ksets_pack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "flowb200_quantise_costs": (C.c_int, [_P, _P, C.c_size_t, C.c_double, C.c_int, _P]),

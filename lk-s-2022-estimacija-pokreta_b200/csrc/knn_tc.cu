@@ -1,0 +1,709 @@
+// Per-cell exact k-NN, tensor-core path (FLOWB200_KNN_TCGEN05).  Replaces generisi's FLANN search
+// (daisy i flann.py:157-189) with an exact one in three steps:
+//
+//  1. knn_prep_*      descriptors -> fp16 GEMM operands (scaled by 64), K = 68 -> 80:
+//                       query row  q' = [ q~(68) | 1 1 1 | 0.. ]           image layout   [H][W][80]
+//                       target row t' = [-t~(68) | n_hi n_mid n_lo | 0.. ] cell-major     [cell][Tpad][80]
+//                     with n = |t~|^2/2 split into three halves, so that q'.t' = |t~|^2/2 - q~.t~ =: a(q,t),
+//                     a monotone function of |q~-t~|^2 for fixed q: the accumulator IS the ranking score.
+//                     Targets of a cell are stored in a decimating permutation (pos -> idx = pos*s mod T) so that
+//                     every run of 32 columns is a spread-out sample of the cell.
+//  2. knn_select_kernel  tcgen05 GEMM (TMA -> smem -> tcgen05.mma -> TMEM, M=128 queries x N=128 targets per MMA
+//                     chunk, fp32 accumulate) with a fused streaming selection epilogue read back with tcgen05.ld:
+//                     every thread owns one query row, keeps the k smallest 32-column group minima (an upper bound
+//                     tau on the k-th smallest score) and appends every score <= tau + 2*eps to a scratch list;
+//                     at the end of the cell the list is filtered with the final tau.  eps bounds |a - exact score|
+//                     rigorously (fp16 rounding residual norms by Cauchy-Schwarz + fp32 accumulation slack), so the
+//                     surviving candidate set provably contains the exact k nearest neighbours (ties included).
+//  3. knn_rerank_kernel  exact float64 distances of the candidates (same arithmetic as the float64 brute force and
+//                     the CPU oracle), rank by (distance, index), write the k proposals + float32 L1 data costs.
+//     knn_fallback_kernel  (query, cell) pairs whose lists overflowed are redone by brute force.
+//
+// One CTA = one 16x8-pixel query tile x one target cell at a time (persistent over a static work list), 6 warps:
+// warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue (one TMEM lane quadrant each).
+// Two CTAs are resident per SM (256 TMEM columns each) so one CTA's selection overlaps the other's MMAs.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace flowb200 {
+
+constexpr int kKP = 80;            // padded contraction depth (5 x k16)
+constexpr int kKB = 5;             // k16 blocks
+constexpr float kScale = 64.0f;    // descriptors are < ~0.5: keeps fp16 values far from subnormals
+constexpr int kTileW = 16, kTileH = 8, kTileM = 128;
+constexpr int kChunkN = 128;       // targets per accumulator stage
+constexpr int kBStages = 3;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = kAccStages * kChunkN;          // 256
+constexpr int kSlabBytes = kTileM * 32;                  // one k16 block of 128 rows: 4096 B
+constexpr int kTileBytes = kKB * kSlabBytes;             // 20480 B
+constexpr int kCollect = 96;       // scratch list entries per query row (overflow -> brute-force fallback)
+constexpr int kCand = 32;          // candidates handed to the exact re-rank per (query, cell)
+constexpr int kSelThreads = 192;
+constexpr float kPadNorm = 60000.0f;   // n_hi of padding target rows: their score can never be selected
+
+struct KnnTcGeom {
+  int H, W, cellw, cellh, ncellx, ncelly, R, K, T, Tpad, stride_s, tiles_x, tiles_y, nblk;
+  float tphi;
+};
+
+// ------------------------------------------------------------------------------------------------
+// 1. operand preparation
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float up(float x) { return __fmul_ru(x, 1.0001f); }   // slack for fp32 rounding in the bounds
+
+// one warp per pixel.  qinfo[pix] = (rq, Nq): rq >= |64 q - q~|_2, Nq >= |q~|_2
+__global__ void knn_prep_query_kernel(const float* __restrict__ desc, int npix, __half* __restrict__ out,
+                                      float2* __restrict__ qinfo) {
+  const int pix = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pix >= npix) return;
+  const float* d = desc + (size_t)pix * kDescDim;
+  __half* o = out + (size_t)pix * kKP;
+  float r2 = 0.f, n2 = 0.f;
+  for (int j = lane; j < kKP; j += 32) {
+    __half h = __float2half_rn(0.f);
+    if (j < kDescDim) {
+      const float v = d[j] * kScale;          // exact (power of two)
+      h = __float2half_rn(v);
+      const float hv = __half2float(h);
+      const float e = v - hv;                 // exact (Sterbenz-like: hv is v rounded to 11 bits)
+      r2 = fmaf(e, e, r2);
+      n2 = fmaf(hv, hv, n2);
+    } else if (j < kDescDim + 3) {
+      h = __float2half_rn(1.0f);
+    }
+    o[j] = h;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    r2 += __shfl_xor_sync(0xffffffffu, r2, off);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+  }
+  if (lane == 0) qinfo[pix] = make_float2(up(sqrtf(up(r2))), up(sqrtf(up(n2))));
+}
+
+// one warp per (cell, pos).  cellinfo[cell] = (max rt, max Nt, max n) as float bit patterns (atomicMax on ints)
+__global__ void knn_prep_target_kernel(const float* __restrict__ desc, KnnTcGeom g, __half* __restrict__ out,
+                                       int* __restrict__ cellinfo) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ncell = g.ncellx * g.ncelly;
+  if (w >= ncell * g.Tpad) return;
+  const int cell = w / g.Tpad, pos = w - cell * g.Tpad;
+  __half* o = out + (size_t)w * kKP;
+  if (pos >= g.T) {   // padding row
+    for (int j = lane; j < kKP; j += 32) o[j] = __float2half_rn(j == kDescDim ? kPadNorm : 0.f);
+    return;
+  }
+  const int idx = (int)(((long long)pos * g.stride_s) % g.T);
+  const int ci = cell % g.ncellx, cj = cell / g.ncellx;
+  const int ty = cj * g.cellh + idx / g.cellw, tx = ci * g.cellw + idx % g.cellw;
+  const float* d = desc + ((size_t)ty * g.W + tx) * kDescDim;
+  float r2 = 0.f, n2 = 0.f, s2 = 0.f;
+  for (int j = lane; j < kDescDim; j += 32) {
+    const float v = d[j] * kScale;
+    const __half h = __float2half_rn(v);
+    const float hv = __half2float(h);
+    const float e = v - hv;
+    r2 = fmaf(e, e, r2);
+    n2 = fmaf(hv, hv, n2);
+    s2 = fmaf(v, v, s2);
+    o[j] = __float2half_rn(-hv);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    r2 += __shfl_xor_sync(0xffffffffu, r2, off);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+  }
+  // n = |t~|^2 / 2 as three halves (residual below 2^-30 n, covered by the accumulation slack in eps)
+  const float n = 0.5f * n2;
+  const __half h0 = __float2half_rn(n);
+  const float r0 = n - __half2float(h0);
+  const __half h1 = __float2half_rn(r0);
+  const float r1 = r0 - __half2float(h1);
+  const __half h2 = __float2half_rn(r1);
+  for (int j = kDescDim + lane; j < kKP; j += 32) {
+    o[j] = j == kDescDim ? h0 : j == kDescDim + 1 ? h1 : j == kDescDim + 2 ? h2 : __float2half_rn(0.f);
+  }
+  if (lane == 0) {
+    // n as computed here differs from the exact |t~|^2/2 by fp32 rounding of n2: folded into rt's slack
+    atomicMax(cellinfo + 4 * cell + 0, __float_as_int(up(sqrtf(up(r2)))));
+    atomicMax(cellinfo + 4 * cell + 1, __float_as_int(up(sqrtf(up(fmaxf(s2, n2))))));
+    atomicMax(cellinfo + 4 * cell + 2, __float_as_int(up(n)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. tcgen05 GEMM + streaming selection
+// ------------------------------------------------------------------------------------------------
+struct SelSmem {
+  uint64_t a_full, a_empty;
+  uint64_t b_full[kBStages], b_empty[kBStages];
+  uint64_t t_full[kAccStages], t_empty[kAccStages];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// insert v into the ascending list (branch free): list keeps its KC smallest values
+template <int KC>
+__device__ __forceinline__ void list_insert(float (&lst)[KC], float v) {
+#pragma unroll
+  for (int j = 0; j < KC; ++j) {
+    const float lo = fminf(lst[j], v);
+    v = fmaxf(lst[j], v);
+    lst[j] = lo;
+  }
+}
+
+// decode a work item; returns false when the tile lies outside the cell's query band
+__device__ __forceinline__ bool decode_item(const KnnTcGeom& g, int item, int& cell, int& qx0, int& qy0, int& x1,
+                                            int& y1) {
+  const int tiles = g.tiles_x * g.tiles_y;
+  cell = item / tiles;
+  const int t = item - cell * tiles;
+  const int tyi = t / g.tiles_x, txi = t - tyi * g.tiles_x;
+  const int ci = cell % g.ncellx, cj = cell / g.ncellx;
+  const int x0 = max(0, g.cellw * (ci - g.R)), y0 = max(0, g.cellh * (cj - g.R));
+  x1 = min(g.W, g.cellw * (ci + g.R + 1));
+  y1 = min(g.H, g.cellh * (cj + g.R + 1));
+  qx0 = x0 + txi * kTileW;
+  qy0 = y0 + tyi * kTileH;
+  return qx0 < x1 && qy0 < y1;
+}
+
+template <int KC>
+__global__ void __launch_bounds__(kSelThreads, 2)
+knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t, KnnTcGeom g,
+                  int n_items, const float2* __restrict__ qinfo, const int* __restrict__ cellinfo,
+                  float2* __restrict__ scratch, uint16_t* __restrict__ cand, uint8_t* __restrict__ cand_cnt,
+                  float* __restrict__ dbg_scores) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kTileBytes;
+  SelSmem* ss = reinterpret_cast<SelSmem*>(smem + kTileBytes * (1 + kBStages));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = g.Tpad / kChunkN;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_q);
+    ptx::prefetch_tmap(&tmap_t);
+    ptx::mbar_init(&ss->a_full, 1);
+    ptx::mbar_init(&ss->a_empty, 1);
+    for (int i = 0; i < kBStages; ++i) {
+      ptx::mbar_init(&ss->b_full[i], 1);
+      ptx::mbar_init(&ss->b_empty[i], 1);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      ptx::mbar_init(&ss->t_full[i], 1);
+      ptx::mbar_init(&ss->t_empty[i], 4);      // one arrival per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<kTmemCols>(&ss->tmem_base);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ss->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0, bcount = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int cell, qx0, qy0, x1, y1;
+        if (!decode_item(g, item, cell, qx0, qy0, x1, y1)) continue;
+        ptx::mbar_wait(&ss->a_empty, (it & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&ss->a_full, kTileBytes);
+#pragma unroll
+        for (int kb = 0; kb < kKB; ++kb) ptx::tma_load_3d(sA + kb * kSlabBytes, &tmap_q, &ss->a_full, kb * 16, qx0, qy0);
+        for (int c = 0; c < nchunks; ++c, ++bcount) {
+          const uint32_t st = bcount % kBStages, ph = (bcount / kBStages) & 1;
+          ptx::mbar_wait(&ss->b_empty[st], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&ss->b_full[st], kTileBytes);
+#pragma unroll
+          for (int kb = 0; kb < kKB; ++kb)
+            ptx::tma_load_3d(sB + st * kTileBytes + kb * kSlabBytes, &tmap_t, &ss->b_full[st], kb * 16, c * kChunkN, cell);
+        }
+        ++it;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_f16(kTileM, kChunkN);
+      uint32_t it = 0, bcount = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int cell, qx0, qy0, x1, y1;
+        if (!decode_item(g, item, cell, qx0, qy0, x1, y1)) continue;
+        ptx::mbar_wait(&ss->a_full, it & 1);
+        for (int c = 0; c < nchunks; ++c, ++bcount) {
+          const uint32_t st = bcount % kBStages, ph = (bcount / kBStages) & 1;
+          const uint32_t acc = bcount % kAccStages, aph = (bcount / kAccStages) & 1;
+          ptx::mbar_wait(&ss->b_full[st], ph);
+          ptx::mbar_wait(&ss->t_empty[acc], aph ^ 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int kb = 0; kb < kKB; ++kb) {
+            const uint64_t da = ptx::umma_desc_k_sw32(ptx::smem_u32(sA + kb * kSlabBytes));
+            const uint64_t db = ptx::umma_desc_k_sw32(ptx::smem_u32(sB + st * kTileBytes + kb * kSlabBytes));
+            ptx::mma_f16_ss(tmem_base + acc * kChunkN, da, db, idesc, kb > 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(&ss->b_empty[st]);     // B stage reusable once these MMAs have read it
+          ptx::mma_commit(&ss->t_full[acc]);     // accumulator stage complete
+        }
+        ptx::mma_commit(&ss->a_empty);           // A tile reusable
+        ++it;
+      }
+    }
+  } else {
+    // ===================== selection epilogue =====================
+    const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;            // query row of the tile = TMEM lane
+    float2* my_scratch = scratch + (size_t)blockIdx.x * kCollect * kTileM + row;
+    uint32_t bcount = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int cell, qx0, qy0, x1, y1;
+      if (!decode_item(g, item, cell, qx0, qy0, x1, y1)) continue;
+      const int px = qx0 + (row & (kTileW - 1)), py = qy0 + (row >> 4);
+      const bool valid = px < x1 && py < y1;
+      const int pix = valid ? py * g.W + px : 0;
+      // eps >= |a - exact score| for every target of the cell (see file header)
+      const float2 qi = qinfo[pix];
+      const float rt = __int_as_float(cellinfo[4 * cell + 0]), nt = __int_as_float(cellinfo[4 * cell + 1]);
+      const float nmax = __int_as_float(cellinfo[4 * cell + 2]);
+      float eps = qi.x * nt + qi.y * rt + rt * (nt + rt) + 2.0e-5f * (qi.y * nt + nmax) + 1.0e-5f * nmax;
+      const float eps2 = 2.0f * up(eps);
+
+      float lst[KC];
+#pragma unroll
+      for (int j = 0; j < KC; ++j) lst[j] = CUDART_INF_F;
+      int cnt = 0;
+      for (int c = 0; c < nchunks; ++c, ++bcount) {
+        const uint32_t acc = bcount % kAccStages, aph = (bcount / kAccStages) & 1;
+        ptx::mbar_wait(&ss->t_full[acc], aph);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int gq = 0; gq < kChunkN / 32; ++gq) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kChunkN + gq * 32, r);
+          ptx::tmem_ld_wait();
+          const int pos0 = c * kChunkN + gq * 32;
+          if (dbg_scores) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              dbg_scores[((size_t)item * kTileM + row) * g.Tpad + pos0 + j] = __uint_as_float(r[j]);
+          }
+          if (c == 0 && gq == 0) {
+            // first 32 scores of the cell: exact element-level list
+#pragma unroll
+            for (int j = 0; j < 32; ++j) list_insert<KC>(lst, __uint_as_float(r[j]));
+          } else {
+            float m[11];
+#pragma unroll
+            for (int j = 0; j < 10; ++j)
+              m[j] = fmin3(__uint_as_float(r[3 * j]), __uint_as_float(r[3 * j + 1]), __uint_as_float(r[3 * j + 2]));
+            m[10] = fminf(__uint_as_float(r[30]), __uint_as_float(r[31]));
+            const float gm = fmin3(fmin3(m[0], m[1], m[2]), fmin3(m[3], m[4], m[5]),
+                                   fmin3(fmin3(m[6], m[7], m[8]), m[9], m[10]));
+            list_insert<KC>(lst, gm);
+          }
+          const float bound = lst[KC - 1] + eps2;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = __uint_as_float(r[j]);
+            if (v <= bound) {
+              if (cnt < kCollect) my_scratch[(size_t)cnt * kTileM] = make_float2(v, __int_as_float(pos0 + j));
+              ++cnt;
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&ss->t_empty[acc]);
+      }
+      // end of the cell: filter with the final bound, emit candidate target indices
+      if (valid) {
+        const int ci = cell % g.ncellx, cj = cell / g.ncellx;
+        int cimin, cimax, cjmin, cjmax;
+        cell_range(px, g.cellw, g.ncellx, g.R, &cimin, &cimax);
+        cell_range(py, g.cellh, g.ncelly, g.R, &cjmin, &cjmax);
+        const int blk = (ci - cimin) * (cjmax - cjmin + 1) + (cj - cjmin);
+        const size_t task = (size_t)pix * g.nblk + blk;
+        const float bound = lst[KC - 1] + eps2;
+        int ns = 0;
+        const int n = min(cnt, kCollect);
+        for (int s = 0; s < n; ++s) {
+          const float2 e = my_scratch[(size_t)s * kTileM];
+          if (e.x <= bound) {
+            if (ns < kCand) {
+              const int pos = __float_as_int(e.y);
+              cand[task * kCand + ns] = (uint16_t)(((long long)pos * g.stride_s) % g.T);
+            }
+            ++ns;
+          }
+        }
+        cand_cnt[task] = (cnt > kCollect || ns > kCand) ? 255 : (uint8_t)ns;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. exact re-rank + data cost.  16 lanes per (query, cell) task, lane = candidate.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double exact_dist(const float* __restrict__ q, const float* __restrict__ t) {
+  double acc = 0.0;
+#pragma unroll
+  for (int d = 0; d < kDescDim; d += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(q + d);
+    const float4 b = *reinterpret_cast<const float4*>(t + d);
+    double e;
+    e = (double)a.x - (double)b.x; acc = __dadd_rn(acc, __dmul_rn(e, e));
+    e = (double)a.y - (double)b.y; acc = __dadd_rn(acc, __dmul_rn(e, e));
+    e = (double)a.z - (double)b.z; acc = __dadd_rn(acc, __dmul_rn(e, e));
+    e = (double)a.w - (double)b.w; acc = __dadd_rn(acc, __dmul_rn(e, e));
+  }
+  return acc;
+}
+
+template <int KC>
+__device__ __forceinline__ void emit_proposal(const KnnTcGeom& g, const float* __restrict__ q, const float* __restrict__ desc_tgt,
+                                              int qx, int qy, int ci, int cj, int blk, int rank, int idx,
+                                              int32_t* __restrict__ pvec, float* __restrict__ lcost,
+                                              int32_t* __restrict__ knn_idx) {
+  const int ty = cj * g.cellh + idx / g.cellw, tx = ci * g.cellw + idx % g.cellw;
+  const float* t = desc_tgt + ((size_t)ty * g.W + tx) * kDescDim;
+  const float s = sum68_numpy_order([&](int d) { return fabsf(__fsub_rn(q[d], t[d])); });
+  const size_t pix = (size_t)qy * g.W + qx;
+  const int slot = KC * blk + rank;
+  pvec[pix * g.K + slot] = pack_vec(ty - qy, tx - qx);
+  lcost[pix * g.K + slot] = s < g.tphi ? s : g.tphi;
+  if (knn_idx) knn_idx[(pix * g.nblk + blk) * KC + rank] = idx;
+}
+
+template <int KC>
+__global__ void __launch_bounds__(256)
+knn_rerank_kernel(const float* __restrict__ desc_src, const float* __restrict__ desc_tgt, KnnTcGeom g,
+                  const uint16_t* __restrict__ cand, const uint8_t* __restrict__ cand_cnt, int32_t* __restrict__ pvec,
+                  float* __restrict__ lcost, int32_t* __restrict__ knn_idx, int32_t* __restrict__ fb_list,
+                  int32_t* __restrict__ fb_count, int fb_cap) {
+  // grid: (query groups of the band, cells); 16 tasks per block of 256 threads
+  const int cell = blockIdx.y;
+  const int ci = cell % g.ncellx, cj = cell / g.ncellx;
+  const int x0 = max(0, g.cellw * (ci - g.R)), x1 = min(g.W, g.cellw * (ci + g.R + 1));
+  const int y0 = max(0, g.cellh * (cj - g.R)), y1 = min(g.H, g.cellh * (cj + g.R + 1));
+  const int bw = x1 - x0, nq = bw * (y1 - y0);
+  const int sub = threadIdx.x & 15;
+  const int qi = blockIdx.x * 16 + (threadIdx.x >> 4);
+  if (qi >= nq) return;
+  const int qy = y0 + qi / bw, qx = x0 + qi % bw;
+  int cimin, cimax, cjmin, cjmax;
+  cell_range(qx, g.cellw, g.ncellx, g.R, &cimin, &cimax);
+  cell_range(qy, g.cellh, g.ncelly, g.R, &cjmin, &cjmax);
+  const int blk = (ci - cimin) * (cjmax - cjmin + 1) + (cj - cjmin);
+  const size_t pix = (size_t)qy * g.W + qx;
+  const size_t task = pix * g.nblk + blk;
+  const int n = cand_cnt[task];
+  const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);
+  if (n == 255) {
+    if (sub == 0) {
+      const int at = atomicAdd(fb_count, 1);
+      if (at < fb_cap) {
+        fb_list[2 * at] = (int)pix;
+        fb_list[2 * at + 1] = cell;
+      }
+    }
+    return;
+  }
+  const float* q = desc_src + pix * kDescDim;
+  const int ty0 = cj * g.cellh, tx0 = ci * g.cellw;
+  // two rounds of 16 candidates
+  double d[2];
+  int id[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = h * 16 + sub;
+    d[h] = CUDART_INF;
+    id[h] = 0x7fffffff;
+    if (c < n) {
+      id[h] = cand[task * kCand + c];
+      const int r = id[h] / g.cellw, cc = id[h] - r * g.cellw;
+      d[h] = exact_dist(q, desc_tgt + ((size_t)(ty0 + r) * g.W + tx0 + cc) * kDescDim);
+    }
+    if (n <= 16) break;
+  }
+  // rank = number of candidates that precede (d, id) lexicographically
+  const int rounds = n <= 16 ? 1 : 2;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (h >= rounds) break;
+    int rank = 0;
+    for (int o = 0; o < rounds; ++o) {
+      for (int l = 0; l < 16; ++l) {
+        const double od = __shfl_sync(gmask, d[o], l, 16);
+        const int oi = __shfl_sync(gmask, id[o], l, 16);
+        rank += (od < d[h] || (od == d[h] && oi < id[h])) ? 1 : 0;
+      }
+    }
+    if (h * 16 + sub < n && rank < KC)
+      emit_proposal<KC>(g, q, desc_tgt, qx, qy, ci, cj, blk, rank, id[h], pvec, lcost, knn_idx);
+  }
+}
+
+// brute force for the (rare) tasks whose candidate lists overflowed: one block per task
+template <int KC>
+__global__ void __launch_bounds__(128)
+knn_fallback_kernel(const float* __restrict__ desc_src, const float* __restrict__ desc_tgt, KnnTcGeom g,
+                    const int32_t* __restrict__ fb_list, const int32_t* __restrict__ fb_count, int fb_cap,
+                    int32_t* __restrict__ pvec, float* __restrict__ lcost, int32_t* __restrict__ knn_idx) {
+  extern __shared__ double fb_d[];       // [T]
+  __shared__ double red_d[4];
+  __shared__ int red_i[4];
+  const int ntask = min(*fb_count, fb_cap);
+  for (int t = blockIdx.x; t < ntask; t += gridDim.x) {
+    const int pix = fb_list[2 * t], cell = fb_list[2 * t + 1];
+    const int qy = pix / g.W, qx = pix - qy * g.W;
+    const int ci = cell % g.ncellx, cj = cell / g.ncellx;
+    const float* q = desc_src + (size_t)pix * kDescDim;
+    const int ty0 = cj * g.cellh, tx0 = ci * g.cellw;
+    __syncthreads();
+    for (int i = threadIdx.x; i < g.T; i += blockDim.x) {
+      const int r = i / g.cellw, c = i - r * g.cellw;
+      fb_d[i] = exact_dist(q, desc_tgt + ((size_t)(ty0 + r) * g.W + tx0 + c) * kDescDim);
+    }
+    __syncthreads();
+    int cimin, cimax, cjmin, cjmax;
+    cell_range(qx, g.cellw, g.ncellx, g.R, &cimin, &cimax);
+    cell_range(qy, g.cellh, g.ncelly, g.R, &cjmin, &cjmax);
+    const int blk = (ci - cimin) * (cjmax - cjmin + 1) + (cj - cjmin);
+    for (int rank = 0; rank < KC; ++rank) {
+      double bd = CUDART_INF;
+      int bi = 0x7fffffff;
+      for (int i = threadIdx.x; i < g.T; i += blockDim.x)
+        if (fb_d[i] < bd) {     // ascending i: strict < keeps the lowest index
+          bd = fb_d[i];
+          bi = i;
+        }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (od < bd || (od == bd && oi < bi)) {
+          bd = od;
+          bi = oi;
+        }
+      }
+      if ((threadIdx.x & 31) == 0) {
+        red_d[threadIdx.x >> 5] = bd;
+        red_i[threadIdx.x >> 5] = bi;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 1; w < 4; ++w)
+          if (red_d[w] < bd || (red_d[w] == bd && red_i[w] < bi)) {
+            bd = red_d[w];
+            bi = red_i[w];
+          }
+        fb_d[bi] = CUDART_INF;
+        emit_proposal<KC>(g, q, desc_tgt, qx, qy, ci, cj, blk, rank, bi, pvec, lcost, knn_idx);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 3-D fp16 tensor map {80 halves, d1, d2}, box {16, b1, b2}, 32-byte swizzle
+static bool make_map(CUtensorMap* m, void* base, uint64_t d1, uint64_t d2, uint32_t b1, uint32_t b2) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)kKP, d1, d2};
+  cuuint64_t strides[2] = {(cuuint64_t)kKP * 2, (cuuint64_t)kKP * 2 * d1};
+  cuuint32_t box[3] = {16, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+         CUDA_SUCCESS;
+}
+
+static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
+
+static KnnTcGeom make_tc_geom(const flowb200_params* p) {
+  KnnTcGeom g;
+  g.H = p->H; g.W = p->W; g.cellw = p->cellw; g.cellh = p->cellh;
+  g.ncellx = p->W / p->cellw; g.ncelly = p->H / p->cellh;
+  g.R = p->cell_radius; g.K = p->maxnprop; g.tphi = p->tphi;
+  g.T = p->cellw * p->cellh;
+  g.Tpad = (g.T + kChunkN - 1) / kChunkN * kChunkN;
+  int s = (int)(0.41421356 * g.T);
+  if (s < 1) s = 1;
+  while (gcd_i(s, g.T) != 1) ++s;
+  g.stride_s = s;
+  const int r = 2 * g.R + 1;
+  g.tiles_x = (min(g.W, r * g.cellw) + kTileW - 1) / kTileW;
+  g.tiles_y = (min(g.H, r * g.cellh) + kTileH - 1) / kTileH;
+  g.nblk = r * r;
+  return g;
+}
+
+struct TcLayout {
+  size_t q16, t16, qinfo, cellinfo, cand, cnt, scratch, fb_list, fb_count, total;
+  int grid, fb_cap;
+};
+
+static TcLayout tc_layout(const flowb200_params* p) {
+  const KnnTcGeom g = make_tc_geom(p);
+  TcLayout L{};
+  const size_t n = (size_t)g.H * g.W, ncell = (size_t)g.ncellx * g.ncelly;
+  size_t off = 0;
+  auto take = [&](size_t b) { size_t o = off; off += align_up(b, 1024); return o; };
+  L.grid = 2 * kNumSMs;
+  L.fb_cap = 1 << 20;
+  L.q16 = take(n * kKP * 2);
+  L.t16 = take(ncell * g.Tpad * kKP * 2);
+  L.qinfo = take(n * sizeof(float2));
+  L.cellinfo = take(ncell * 4 * sizeof(int));
+  L.cand = take(n * g.nblk * kCand * sizeof(uint16_t));
+  L.cnt = take(n * g.nblk);
+  L.scratch = take((size_t)L.grid * kCollect * kTileM * sizeof(float2));
+  L.fb_list = take((size_t)L.fb_cap * 2 * sizeof(int32_t));
+  L.fb_count = take(256);
+  L.total = off;
+  return L;
+}
+
+size_t knn_tc_workspace_bytes(const flowb200_params* p) { return tc_layout(p).total; }
+
+bool knn_tc_supported(const flowb200_params* p) {
+  const int T = p->cellw * p->cellh;
+  return T >= 32 && T <= 65535 && (p->k_cell == 5 || p->k_cell == 10 || p->k_cell == 12) && p->k_cell <= 16 &&
+         T >= p->k_cell;
+}
+
+template <int KC>
+static int run_tc(const float* desc_src, const float* desc_tgt, const flowb200_params* p, const KnnTcGeom& g,
+                  const TcLayout& L, char* ws, int32_t* pvec, float* lcost, int32_t* knn_idx, int32_t* stats,
+                  float* dbg_scores, cudaStream_t stream) {
+  const size_t n = (size_t)g.H * g.W;
+  const int ncell = g.ncellx * g.ncelly;
+  __half* q16 = reinterpret_cast<__half*>(ws + L.q16);
+  __half* t16 = reinterpret_cast<__half*>(ws + L.t16);
+  float2* qinfo = reinterpret_cast<float2*>(ws + L.qinfo);
+  int* cellinfo = reinterpret_cast<int*>(ws + L.cellinfo);
+  uint16_t* cand = reinterpret_cast<uint16_t*>(ws + L.cand);
+  uint8_t* cnt = reinterpret_cast<uint8_t*>(ws + L.cnt);
+  float2* scratch = reinterpret_cast<float2*>(ws + L.scratch);
+  int32_t* fb_list = reinterpret_cast<int32_t*>(ws + L.fb_list);
+  int32_t* fb_count = reinterpret_cast<int32_t*>(ws + L.fb_count);
+
+  FB_CUDA_CHECK(cudaMemsetAsync(cellinfo, 0, (size_t)ncell * 4 * sizeof(int), stream));
+  FB_CUDA_CHECK(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), stream));
+  knn_prep_query_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(desc_src, (int)n, q16, qinfo);
+  FB_LAUNCH_CHECK();
+  const size_t tw = (size_t)ncell * g.Tpad;
+  knn_prep_target_kernel<<<(unsigned)((tw * 32 + 255) / 256), 256, 0, stream>>>(desc_tgt, g, t16, cellinfo);
+  FB_LAUNCH_CHECK();
+
+  CUtensorMap mq, mt;
+  if (!make_map(&mq, q16, (uint64_t)g.W, (uint64_t)g.H, kTileW, kTileH)) return FLOWB200_ECUDA;
+  if (!make_map(&mt, t16, (uint64_t)g.Tpad, (uint64_t)ncell, kChunkN, 1)) return FLOWB200_ECUDA;
+  const int n_items = ncell * g.tiles_x * g.tiles_y;
+  const size_t smem = (size_t)kTileBytes * (1 + kBStages) + sizeof(SelSmem) + 1024;
+  auto kern = knn_select_kernel<KC>;
+  FB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = min(L.grid, n_items);
+  kern<<<grid, kSelThreads, smem, stream>>>(mq, mt, g, n_items, qinfo, cellinfo, scratch, cand, cnt, dbg_scores);
+  FB_LAUNCH_CHECK();
+
+  const int r = 2 * g.R + 1;
+  const int maxq = min(g.W, r * g.cellw) * min(g.H, r * g.cellh);
+  dim3 rgrid((maxq + 15) / 16, ncell);
+  knn_rerank_kernel<KC><<<rgrid, 256, 0, stream>>>(desc_src, desc_tgt, g, cand, cnt, pvec, lcost, knn_idx, fb_list,
+                                                    fb_count, L.fb_cap);
+  FB_LAUNCH_CHECK();
+  auto fkern = knn_fallback_kernel<KC>;
+  const size_t fsmem = (size_t)g.T * sizeof(double);
+  if (fsmem > 48 * 1024) FB_CUDA_CHECK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+  fkern<<<4 * kNumSMs, 128, fsmem, stream>>>(desc_src, desc_tgt, g, fb_list, fb_count, L.fb_cap, pvec, lcost, knn_idx);
+  FB_LAUNCH_CHECK();
+  if (stats) FB_CUDA_CHECK(cudaMemcpyAsync(stats, fb_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  (void)p;
+  return FLOWB200_OK;
+}
+
+int knn_tc_dispatch(const float* desc_src, const float* desc_tgt, const flowb200_params* p, int32_t* pvec, float* lcost,
+                    int32_t* knn_idx, int32_t* stats, float* dbg_scores, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream) {
+  if (!knn_tc_supported(p)) return FLOWB200_EUNSUPPORTED;
+  const TcLayout L = tc_layout(p);
+  if (workspace_bytes < L.total) return FLOWB200_EWORKSPACE;
+  const KnnTcGeom g = make_tc_geom(p);
+  char* ws = static_cast<char*>(workspace);
+  switch (p->k_cell) {
+    case 5: return run_tc<5>(desc_src, desc_tgt, p, g, L, ws, pvec, lcost, knn_idx, stats, dbg_scores, stream);
+    case 10: return run_tc<10>(desc_src, desc_tgt, p, g, L, ws, pvec, lcost, knn_idx, stats, dbg_scores, stream);
+    case 12: return run_tc<12>(desc_src, desc_tgt, p, g, L, ws, pvec, lcost, knn_idx, stats, dbg_scores, stream);
+    default: return FLOWB200_EUNSUPPORTED;
+  }
+}
+
+int knn_tc_debug_scores(const float* desc_src, const float* desc_tgt, const flowb200_params* p, float* scores,
+                        int32_t* geom_out_host, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (!knn_tc_supported(p)) return FLOWB200_EUNSUPPORTED;
+  const TcLayout L = tc_layout(p);
+  const KnnTcGeom g = make_tc_geom(p);
+  if (geom_out_host) {
+    geom_out_host[0] = g.Tpad; geom_out_host[1] = g.stride_s; geom_out_host[2] = g.tiles_x;
+    geom_out_host[3] = g.tiles_y; geom_out_host[4] = g.ncellx * g.ncelly * g.tiles_x * g.tiles_y;
+    geom_out_host[5] = kTileW; geom_out_host[6] = kTileH; geom_out_host[7] = kCand;
+  }
+  if (!scores) return FLOWB200_OK;
+  if (workspace_bytes < L.total) return FLOWB200_EWORKSPACE;
+  const size_t n = (size_t)g.H * g.W;   // the proposals of this diagnostic run go to a throw-away allocation
+  int32_t* pvec = nullptr;
+  float* lcost = nullptr;
+  FB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&pvec), n * g.K * sizeof(int32_t)));
+  FB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&lcost), n * g.K * sizeof(float)));
+  int rc = knn_tc_dispatch(desc_src, desc_tgt, p, pvec, lcost, nullptr, nullptr, scores, workspace, workspace_bytes,
+                           stream);
+  cudaStreamSynchronize(stream);
+  cudaFree(pvec);
+  cudaFree(lcost);
+  return rc;
+}
+
+}  // namespace flowb200

@@ -353,25 +353,48 @@ int finish_nn(const flowb200_params* p, int32_t* pvec, float* lcost, int32_t* np
   return FLOWB200_OK;
 }
 
+// knn_tc.cu
+size_t knn_tc_workspace_bytes(const flowb200_params* p);
+bool knn_tc_supported(const flowb200_params* p);
+int knn_tc_dispatch(const float* desc_src, const float* desc_tgt, const flowb200_params* p, int32_t* pvec, float* lcost,
+                    int32_t* knn_idx, int32_t* stats, float* dbg_scores, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream);
+int knn_tc_debug_scores(const float* desc_src, const float* desc_tgt, const flowb200_params* p, float* scores,
+                        int32_t* geom_out_host, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 }  // namespace flowb200
 
 using namespace flowb200;
 
 extern "C" size_t flowb200_knn_workspace_bytes(const flowb200_params* p) {
-  (void)p;
+  if (!p || check_params(p)) return 0;
+  if (p->knn_mode == FLOWB200_KNN_TCGEN05 && knn_tc_supported(p)) return knn_tc_workspace_bytes(p);
   return 256;   // the exact float64 search needs no scratch
+}
+
+extern "C" int flowb200_knn_debug_scores(const float* desc_src, const float* desc_tgt, const flowb200_params* p,
+                                         float* scores, int32_t* geom_out_host, void* workspace,
+                                         size_t workspace_bytes, flowb200_stream_t stream) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  return knn_tc_debug_scores(desc_src, desc_tgt, p, scores, geom_out_host, workspace, workspace_bytes, stream);
 }
 
 extern "C" int flowb200_knn_proposals(const float* desc_src, const float* desc_tgt, const flowb200_params* p,
                                       int32_t* pvec, float* lcost, int32_t* nprop, int32_t* labels, int32_t* knn_idx,
                                       int32_t* stats, void* workspace, size_t workspace_bytes,
                                       flowb200_stream_t stream) {
-  (void)workspace; (void)workspace_bytes; (void)stats;
   int rc = check_params(p);
   if (rc) return rc;
   if (!desc_src || !desc_tgt || !pvec || !lcost || !nprop || !labels) return FLOWB200_EINVAL;
-  if (p->knn_mode != FLOWB200_KNN_EXACT_FP64) return FLOWB200_EUNSUPPORTED;
-  rc = knn_exact_dispatch(desc_src, desc_tgt, p, pvec, lcost, knn_idx, stream);
+  if (p->knn_mode == FLOWB200_KNN_TCGEN05) {
+    if (!workspace) return FLOWB200_EINVAL;
+    rc = knn_tc_dispatch(desc_src, desc_tgt, p, pvec, lcost, knn_idx, stats, nullptr, workspace, workspace_bytes, stream);
+  } else if (p->knn_mode == FLOWB200_KNN_EXACT_FP64) {
+    rc = knn_exact_dispatch(desc_src, desc_tgt, p, pvec, lcost, knn_idx, stream);
+  } else {
+    return FLOWB200_EINVAL;
+  }
   if (rc) return rc;
   return finish_nn(p, pvec, lcost, nprop, labels, knn_idx, stream);
 }

@@ -187,3 +187,22 @@ def pair_workspace(p: FlowParams, device, bcd_mode=_lib.BCD_FP64_F32COST):
     lib = _lib.load()
     cp = cparams(p, bcd_mode=bcd_mode)
     return _workspace(lib.flowb200_pair_workspace_bytes(C.byref(cp)), device)
+
+
+def knn_debug_scores(desc_src, desc_tgt, p: FlowParams):
+    """Diagnostics of the tcgen05 prefilter: (scores float32 [n_items][128][Tpad], geom dict)."""
+    import numpy as np
+    lib = _lib.load()
+    cp = cparams(p, knn_mode=_lib.KNN_TCGEN05)
+    geom = np.zeros(8, dtype=np.int32)
+    _lib.check(lib.flowb200_knn_debug_scores(_ptr(desc_src, torch.float32), _ptr(desc_tgt, torch.float32), C.byref(cp),
+                                             C.c_void_p(0), C.c_void_p(geom.ctypes.data), C.c_void_p(0), 0, _stream()),
+               "flowb200_knn_debug_scores(geom)")
+    names = ("Tpad", "stride_s", "tiles_x", "tiles_y", "n_items", "tile_w", "tile_h", "max_cand")
+    g = {k: int(v) for k, v in zip(names, geom)}
+    scores = torch.full((g["n_items"], 128, g["Tpad"]), float("nan"), dtype=torch.float32, device=desc_src.device)
+    ws = _workspace(lib.flowb200_knn_workspace_bytes(C.byref(cp)), desc_src.device)
+    _lib.check(lib.flowb200_knn_debug_scores(_ptr(desc_src, torch.float32), _ptr(desc_tgt, torch.float32), C.byref(cp),
+                                             _ptr(scores), C.c_void_p(geom.ctypes.data), _ptr(ws), ws.numel(), _stream()),
+               "flowb200_knn_debug_scores")
+    return scores, g

@@ -12,7 +12,7 @@ from helpers import load_case, load_npz, oracle_params, pkg
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-KNN_MODES = [0]       # 1 (tcgen05 prefilter) is added when that kernel lands
+KNN_MODES = [0, 1]    # 0 = float64 CUDA cores, 1 = tcgen05 prefilter + exact re-rank
 DAISY_RTOL = 1e-4      # BASELINE.json north_star: "DAISY must agree within 1e-4 relative"
 
 
@@ -157,6 +157,52 @@ def test_knn_indices_bit_exact(knn_mode, k_cell):
     assert np.array_equal(ioc.unpack_proposals(pvec.cpu().numpy()), P)
     assert np.array_equal(lcost.cpu().numpy().astype(np.float64), L)
     assert np.array_equal(labels.cpu().numpy(), B)
+
+
+def test_tcgen05_scores_match_fp16_operands():
+    """Raw tensor-core ranking scores (TMA + UMMA descriptors + TMEM read-back) against numpy on the same fp16
+    operands: a(q,t) = |t~|^2/2 - q~.t~ with q~, t~ = fp16(64*d), targets in the pos -> pos*s mod T order."""
+    from oracle import daisy as od
+    ops = pkg("ops")
+    H, W, cw, ch = 40, 48, 12, 10
+    img1, img2, _, _ = pkg("synth").make_pair(H, W, 7, max_dx=4, max_dy=3, n_rect=1)
+    d1, d2 = od.daisy(img1), od.daisy(img2)
+    p = pkg("params").FlowParams(H=H, W=W, cellw=cw, cellh=ch, knn_mode=1)
+    scores, g = ops.knn_debug_scores(dev(d1), dev(d2), p)
+    scores = scores.cpu().numpy()
+    T, Tpad, s = cw * ch, g["Tpad"], g["stride_s"]
+    ncx, ncy, R = W // cw, H // ch, p.cell_radius
+    q16 = (d1 * np.float32(64)).astype(np.float16).astype(np.float64)
+    checked = 0
+    for cell in range(ncx * ncy):
+        ci, cj = cell % ncx, cell // ncx
+        idx = (np.arange(T) * s) % T
+        tg = d2[cj * ch + idx // cw, ci * cw + idx % cw]
+        t16 = (tg * np.float32(64)).astype(np.float16).astype(np.float64)
+        n = (0.5 * (t16 ** 2).sum(1)).astype(np.float32)
+        h0 = n.astype(np.float16).astype(np.float32)
+        h1 = (n - h0).astype(np.float16).astype(np.float32)
+        h2 = (n - h0 - h1).astype(np.float16).astype(np.float32)
+        nn = h0.astype(np.float64) + h1 + h2
+        x0, x1 = max(0, cw * (ci - R)), min(W, cw * (ci + R + 1))
+        y0, y1 = max(0, ch * (cj - R)), min(H, ch * (cj + R + 1))
+        for tyi in range(g["tiles_y"]):
+            for txi in range(g["tiles_x"]):
+                qx0, qy0 = x0 + txi * 16, y0 + tyi * 8
+                item = cell * g["tiles_x"] * g["tiles_y"] + tyi * g["tiles_x"] + txi
+                if qx0 >= x1 or qy0 >= y1:
+                    assert np.isnan(scores[item]).all()          # skipped work item
+                    continue
+                for row in (0, 17, 127, 64):
+                    px, py = qx0 + (row & 15), qy0 + (row >> 4)
+                    if px >= W or py >= H:
+                        continue                                  # zero-filled TMA rows
+                    want = nn - t16 @ q16[py, px]
+                    got = scores[item, row, :T]
+                    assert np.abs(got - want).max() < 2e-3, (cell, txi, tyi, row, np.abs(got - want).max())
+                    assert (scores[item, row, T:] > 5e4).all()    # padding columns can never be selected
+                    checked += 1
+    assert checked > 100
 
 
 def test_random_proposals_philox_statistics():
