@@ -88,7 +88,8 @@ int flowb200_daisy(const uint8_t* bgr, int H, int W, float* desc, void* workspac
  *   pvec int32 [H][W][K], lcost float32 [H][W][K], nprop int32 [H][W], labels int32 [H][W]
  *   knn_idx (optional, may be NULL): int32 [H][W][(2r+1)^2][k_cell] target index inside the cell
  *       (idx = row*cellw + col, :147-148), -1 for cells out of range; block order = slot order.
- *   stats (optional): int32[4] device counters {uncertified (query,cell) pairs re-done exactly, ...}. */
+ *   stats (optional): int32[8] device counters of the tcgen05 path {tasks redone by brute force, collect-list
+ *       overflows, candidate-list overflows, 0, sum of candidates handed to the re-rank, sum of collected scores}. */
 size_t flowb200_knn_workspace_bytes(const flowb200_params* p);
 int flowb200_knn_proposals(const float* desc_src, const float* desc_tgt, const flowb200_params* p,
                            int32_t* pvec, float* lcost, int32_t* nprop, int32_t* labels, int32_t* knn_idx,

@@ -2,17 +2,19 @@
 // (daisy i flann.py:157-189) with an exact one in three steps:
 //
 //  1. knn_prep_*      descriptors -> fp16 GEMM operands (scaled by 64), K = 68 -> 80:
-//                       query row  q' = [ q~(68) | 1 1 1 | 0.. ]           image layout   [H][W][80]
-//                       target row t' = [-t~(68) | n_hi n_mid n_lo | 0.. ] cell-major     [cell][Tpad][80]
-//                     with n = |t~|^2/2 split into three halves, so that q'.t' = |t~|^2/2 - q~.t~ =: a(q,t),
-//                     a monotone function of |q~-t~|^2 for fixed q: the accumulator IS the ranking score.
+//                       query row  q' = [ q~(68) | 1 1 1 | m_hi m_mid m_lo | 0.. ]   image layout [H][W][80]
+//                       target row t' = [-t~(68) | n_hi n_mid n_lo | 1 1 1 | 0.. ]   cell-major   [cell][Tpad][80]
+//                     with n = |t~|^2/2 and m = |q~|^2/2 split into three halves each, so that
+//                     q'.t' = |q~|^2/2 + |t~|^2/2 - q~.t~ = |q~-t~|^2/2 =: a(q,t) >= 0: the accumulator IS the
+//                     ranking score (m only shifts a row; it cancels in every comparison).
 //                     Targets of a cell are stored in a decimating permutation (pos -> idx = pos*s mod T) so that
 //                     every run of 32 columns is a spread-out sample of the cell.
 //  2. knn_select_kernel  tcgen05 GEMM (TMA -> smem -> tcgen05.mma -> TMEM, M=128 queries x N=128 targets per MMA
 //                     chunk, fp32 accumulate) with a fused streaming selection epilogue read back with tcgen05.ld:
 //                     every thread owns one query row, keeps the k smallest 32-column group minima (an upper bound
-//                     tau on the k-th smallest score) and appends every score <= tau + 2*eps to a scratch list;
-//                     at the end of the cell the list is filtered with the final tau.  eps bounds |a - exact score|
+//                     tau on the k-th smallest score) and appends every score <= tau + 2*eps to a shared-memory
+//                     list (compacted with the current tau when it fills); at the end of the cell the list is
+//                     filtered with the final tau.  eps bounds |a - exact score|
 //                     rigorously (fp16 rounding residual norms by Cauchy-Schwarz + fp32 accumulation slack), so the
 //                     surviving candidate set provably contains the exact k nearest neighbours (ties included).
 //  3. knn_rerank_kernel  exact float64 distances of the candidates (same arithmetic as the float64 brute force and
@@ -36,12 +38,12 @@ constexpr int kKB = 5;             // k16 blocks
 constexpr float kScale = 64.0f;    // descriptors are < ~0.5: keeps fp16 values far from subnormals
 constexpr int kTileW = 16, kTileH = 8, kTileM = 128;
 constexpr int kChunkN = 128;       // targets per accumulator stage
-constexpr int kBStages = 3;
+constexpr int kBStages = 2;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * kChunkN;          // 256
 constexpr int kSlabBytes = kTileM * 32;                  // one k16 block of 128 rows: 4096 B
 constexpr int kTileBytes = kKB * kSlabBytes;             // 20480 B
-constexpr int kCollect = 96;       // scratch list entries per query row (overflow -> brute-force fallback)
+constexpr int kListCap = 96;       // per-row candidate list in shared memory (compacted when > kListCap - 8)
 constexpr int kCand = 32;          // candidates handed to the exact re-rank per (query, cell)
 constexpr int kSelThreads = 192;
 constexpr float kPadNorm = 60000.0f;   // n_hi of padding target rows: their score can never be selected
@@ -77,14 +79,25 @@ __global__ void knn_prep_query_kernel(const float* __restrict__ desc, int npix, 
     } else if (j < kDescDim + 3) {
       h = __float2half_rn(1.0f);
     }
-    o[j] = h;
+    if (j < kDescDim + 3 || j >= kDescDim + 6) o[j] = h;
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     r2 += __shfl_xor_sync(0xffffffffu, r2, off);
     n2 += __shfl_xor_sync(0xffffffffu, n2, off);
   }
-  if (lane == 0) qinfo[pix] = make_float2(up(sqrtf(up(r2))), up(sqrtf(up(n2))));
+  if (lane == 0) {
+    qinfo[pix] = make_float2(up(sqrtf(up(r2))), up(sqrtf(up(n2))));
+    // slots 71..73: |q~|^2/2 in three halves (times the target's 1s): shifts every score of this row by the
+    // same amount, which makes a = |q~ - t~|^2 / 2 >= 0 without changing the ranking
+    const float nq = 0.5f * n2;
+    const __half h0 = __float2half_rn(nq);
+    const float r0 = nq - __half2float(h0);
+    const __half h1 = __float2half_rn(r0);
+    o[kDescDim + 3] = h0;
+    o[kDescDim + 4] = h1;
+    o[kDescDim + 5] = __float2half_rn(r0 - __half2float(h1));
+  }
 }
 
 // one warp per (cell, pos).  cellinfo[cell] = (max rt, max Nt, max n) as float bit patterns (atomicMax on ints)
@@ -129,7 +142,8 @@ __global__ void knn_prep_target_kernel(const float* __restrict__ desc, KnnTcGeom
   const float r1 = r0 - __half2float(h1);
   const __half h2 = __float2half_rn(r1);
   for (int j = kDescDim + lane; j < kKP; j += 32) {
-    o[j] = j == kDescDim ? h0 : j == kDescDim + 1 ? h1 : j == kDescDim + 2 ? h2 : __float2half_rn(0.f);
+    o[j] = j == kDescDim ? h0 : j == kDescDim + 1 ? h1 : j == kDescDim + 2 ? h2
+           : j < kDescDim + 6 ? __float2half_rn(1.0f) : __float2half_rn(0.f);
   }
   if (lane == 0) {
     // n as computed here differs from the exact |t~|^2/2 by fp32 rounding of n2: folded into rt's slack
@@ -166,6 +180,16 @@ __device__ __forceinline__ void list_insert(float (&lst)[KC], float v) {
   }
 }
 
+// filter a row's shared-memory candidate list in place with the current bound; returns the new length
+__device__ __noinline__ int list_compact(uint32_t* lst, int cnt, float bound) {
+  int m = 0;
+  for (int e = 0; e < cnt; ++e) {
+    const uint32_t en = lst[e * kTileM];
+    if (__uint_as_float(en & 0xFFFFF800u) <= bound) lst[(m++) * kTileM] = en;
+  }
+  return m;
+}
+
 // decode a work item; returns false when the tile lies outside the cell's query band
 __device__ __forceinline__ bool decode_item(const KnnTcGeom& g, int item, int& cell, int& qx0, int& qy0, int& x1,
                                             int& y1) {
@@ -186,13 +210,14 @@ template <int KC>
 __global__ void __launch_bounds__(kSelThreads, 2)
 knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t, KnnTcGeom g,
                   int n_items, const float2* __restrict__ qinfo, const int* __restrict__ cellinfo,
-                  float2* __restrict__ scratch, uint16_t* __restrict__ cand, uint8_t* __restrict__ cand_cnt,
-                  float* __restrict__ dbg_scores) {
+                  uint16_t* __restrict__ cand, uint8_t* __restrict__ cand_cnt, int32_t* __restrict__ counters,
+                  int counters_on, float* __restrict__ dbg_scores) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + kTileBytes;
-  SelSmem* ss = reinterpret_cast<SelSmem*>(smem + kTileBytes * (1 + kBStages));
+  uint32_t* list_e = reinterpret_cast<uint32_t*>(smem + kTileBytes * (1 + kBStages));      // [kListCap][128]
+  SelSmem* ss = reinterpret_cast<SelSmem*>(list_e + kListCap * kTileM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = g.Tpad / kChunkN;
@@ -225,13 +250,13 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int cell, qx0, qy0, x1, y1;
         if (!decode_item(g, item, cell, qx0, qy0, x1, y1)) continue;
-        ptx::mbar_wait(&ss->a_empty, (it & 1) ^ 1);
+        ptx::mbar_wait_backoff(&ss->a_empty, (it & 1) ^ 1, 64);
         ptx::mbar_arrive_expect_tx(&ss->a_full, kTileBytes);
 #pragma unroll
         for (int kb = 0; kb < kKB; ++kb) ptx::tma_load_3d(sA + kb * kSlabBytes, &tmap_q, &ss->a_full, kb * 16, qx0, qy0);
         for (int c = 0; c < nchunks; ++c, ++bcount) {
           const uint32_t st = bcount % kBStages, ph = (bcount / kBStages) & 1;
-          ptx::mbar_wait(&ss->b_empty[st], ph ^ 1);
+          ptx::mbar_wait_backoff(&ss->b_empty[st], ph ^ 1, 64);
           ptx::mbar_arrive_expect_tx(&ss->b_full[st], kTileBytes);
 #pragma unroll
           for (int kb = 0; kb < kKB; ++kb)
@@ -248,12 +273,12 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int cell, qx0, qy0, x1, y1;
         if (!decode_item(g, item, cell, qx0, qy0, x1, y1)) continue;
-        ptx::mbar_wait(&ss->a_full, it & 1);
+        ptx::mbar_wait_backoff(&ss->a_full, it & 1, 32);
         for (int c = 0; c < nchunks; ++c, ++bcount) {
           const uint32_t st = bcount % kBStages, ph = (bcount / kBStages) & 1;
           const uint32_t acc = bcount % kAccStages, aph = (bcount / kAccStages) & 1;
-          ptx::mbar_wait(&ss->b_full[st], ph);
-          ptx::mbar_wait(&ss->t_empty[acc], aph ^ 1);
+          ptx::mbar_wait_backoff(&ss->b_full[st], ph, 32);
+          ptx::mbar_wait_backoff(&ss->t_empty[acc], aph ^ 1, 32);
           ptx::tc_fence_after();
 #pragma unroll
           for (int kb = 0; kb < kKB; ++kb) {
@@ -272,7 +297,8 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     // ===================== selection epilogue =====================
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;            // query row of the tile = TMEM lane
-    float2* my_scratch = scratch + (size_t)blockIdx.x * kCollect * kTileM + row;
+    uint32_t* my_list = list_e + row;            // candidate list of this row: [entry][row]
+    const uint32_t list_base = ptx::smem_u32(my_list);
     uint32_t bcount = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int cell, qx0, qy0, x1, y1;
@@ -284,56 +310,93 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       const float2 qi = qinfo[pix];
       const float rt = __int_as_float(cellinfo[4 * cell + 0]), nt = __int_as_float(cellinfo[4 * cell + 1]);
       const float nmax = __int_as_float(cellinfo[4 * cell + 2]);
-      float eps = qi.x * nt + qi.y * rt + rt * (nt + rt) + 2.0e-5f * (qi.y * nt + nmax) + 1.0e-5f * nmax;
+      const float eps = qi.x * nt + qi.y * rt + rt * (nt + rt) + 2.0e-5f * (qi.y * nt + nmax) + 1.0e-5f * nmax;
       const float eps2 = 2.0f * up(eps);
 
       float lst[KC];
 #pragma unroll
       for (int j = 0; j < KC; ++j) lst[j] = CUDART_INF_F;
-      int cnt = 0;
-      for (int c = 0; c < nchunks; ++c, ++bcount) {
-        const uint32_t acc = bcount % kAccStages, aph = (bcount / kAccStages) & 1;
-        ptx::mbar_wait(&ss->t_full[acc], aph);
-        ptx::tc_fence_after();
-#pragma unroll 1
-        for (int gq = 0; gq < kChunkN / 32; ++gq) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kChunkN + gq * 32, r);
-          ptx::tmem_ld_wait();
-          const int pos0 = c * kChunkN + gq * 32;
-          if (dbg_scores) {
+      bool overflow = false;
+
+      // One group = 32 consecutive score columns of this row, already in registers.  List entries are the
+      // score with its 11 low mantissa bits replaced by the column position (scores are >= 0 up to rounding,
+      // so the truncated score is <= the score: later filters on the stored value keep a superset).
+      uint32_t waddr = list_base;               // shared address of the next free entry of this row
+      auto process = [&](const uint32_t (&r)[32], int pos0, bool first) {
+        if (dbg_scores) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              dbg_scores[((size_t)item * kTileM + row) * g.Tpad + pos0 + j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j)
+            dbg_scores[((size_t)item * kTileM + row) * g.Tpad + pos0 + j] = __uint_as_float(r[j]);
+        }
+        if (first) {   // first group of the cell: 16 pair minima (distinct elements) seed the list
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            list_insert<KC>(lst, fminf(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])));
+        } else {
+          float m[11];
+#pragma unroll
+          for (int j = 0; j < 10; ++j)
+            m[j] = fmin3(__uint_as_float(r[3 * j]), __uint_as_float(r[3 * j + 1]), __uint_as_float(r[3 * j + 2]));
+          m[10] = fminf(__uint_as_float(r[30]), __uint_as_float(r[31]));
+          const float gm = fmin3(fmin3(m[0], m[1], m[2]), fmin3(m[3], m[4], m[5]),
+                                 fmin3(fmin3(m[6], m[7], m[8]), m[9], m[10]));
+          list_insert<KC>(lst, gm);
+        }
+        const float bound = lst[KC - 1] + eps2;
+#pragma unroll
+        for (int j8 = 0; j8 < 32; j8 += 8) {
+#pragma unroll
+          for (int j = j8; j < j8 + 8; ++j) {
+            const uint32_t tagged = (r[j] & 0xFFFFF800u) + (uint32_t)(pos0 + j);
+            // predicated append (no branch): room for 8 more entries is guaranteed by the compaction below
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "setp.le.f32 p, %1, %2;\n\t"
+                "@p st.shared.b32 [%0], %3;\n\t"
+                "@p add.u32 %0, %0, 512;\n\t"
+                "}\n"
+                : "+r"(waddr)
+                : "f"(__uint_as_float(r[j])), "f"(bound), "r"(tagged)
+                : "memory");
           }
-          if (c == 0 && gq == 0) {
-            // first 32 scores of the cell: exact element-level list
-#pragma unroll
-            for (int j = 0; j < 32; ++j) list_insert<KC>(lst, __uint_as_float(r[j]));
-          } else {
-            float m[11];
-#pragma unroll
-            for (int j = 0; j < 10; ++j)
-              m[j] = fmin3(__uint_as_float(r[3 * j]), __uint_as_float(r[3 * j + 1]), __uint_as_float(r[3 * j + 2]));
-            m[10] = fminf(__uint_as_float(r[30]), __uint_as_float(r[31]));
-            const float gm = fmin3(fmin3(m[0], m[1], m[2]), fmin3(m[3], m[4], m[5]),
-                                   fmin3(fmin3(m[6], m[7], m[8]), m[9], m[10]));
-            list_insert<KC>(lst, gm);
-          }
-          const float bound = lst[KC - 1] + eps2;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float v = __uint_as_float(r[j]);
-            if (v <= bound) {
-              if (cnt < kCollect) my_scratch[(size_t)cnt * kTileM] = make_float2(v, __int_as_float(pos0 + j));
-              ++cnt;
+          if (__any_sync(0xffffffffu, waddr > list_base + (kListCap - 8) * 512)) {
+            // whole warp: drop what today's tighter bound already excludes
+            waddr = list_base + 512 * list_compact(my_list, (int)((waddr - list_base) >> 9), bound);
+            if (waddr > list_base + (kListCap - 8) * 512) {   // more than that inside the band: brute force later
+              overflow = true;
+              waddr = list_base;
             }
           }
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&ss->t_empty[acc]);
+      };
+
+      for (int c = 0; c < nchunks; ++c, ++bcount) {
+        const uint32_t acc = bcount % kAccStages, aph = (bcount / kAccStages) & 1;
+        ptx::mbar_wait_backoff(&ss->t_full[acc], aph, 20);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kChunkN;
+        const int cpos = c * kChunkN;
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld_32x32(taddr, r0);
+        ptx::tmem_ld_wait();
+#pragma unroll 1
+        for (int h = 0; h < kChunkN / 64; ++h) {
+          ptx::tmem_ld_32x32(taddr + 64 * h + 32, r1);      // in flight while r0 is processed
+          process(r0, cpos + 64 * h, c == 0 && h == 0);
+          ptx::tmem_ld_wait();
+          if (h + 1 < kChunkN / 64) {
+            ptx::tmem_ld_32x32(taddr + 64 * h + 64, r0);
+          } else {
+            ptx::tc_fence_before();                          // all TMEM reads of this stage are done
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&ss->t_empty[acc]);
+          }
+          process(r1, cpos + 64 * h + 32, false);
+          ptx::tmem_ld_wait();
+        }
       }
+      const int cnt = (int)((waddr - list_base) >> 9);
       // end of the cell: filter with the final bound, emit candidate target indices
       if (valid) {
         const int ci = cell % g.ncellx, cj = cell / g.ncellx;
@@ -344,18 +407,17 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const size_t task = (size_t)pix * g.nblk + blk;
         const float bound = lst[KC - 1] + eps2;
         int ns = 0;
-        const int n = min(cnt, kCollect);
-        for (int s = 0; s < n; ++s) {
-          const float2 e = my_scratch[(size_t)s * kTileM];
-          if (e.x <= bound) {
-            if (ns < kCand) {
-              const int pos = __float_as_int(e.y);
-              cand[task * kCand + ns] = (uint16_t)(((long long)pos * g.stride_s) % g.T);
-            }
+        for (int e = 0; e < cnt; ++e) {
+          const uint32_t en = my_list[e * kTileM];
+          if (__uint_as_float(en & 0xFFFFF800u) <= bound) {
+            if (ns < kCand) cand[task * kCand + ns] = (uint16_t)(((en & 0x7FFu) * (uint32_t)g.stride_s) % (uint32_t)g.T);
             ++ns;
           }
         }
-        cand_cnt[task] = (cnt > kCollect || ns > kCand) ? 255 : (uint8_t)ns;
+        cand_cnt[task] = (overflow || ns > kCand) ? 255 : (uint8_t)ns;
+        if (overflow) atomicAdd(counters + 1, 1);          // diagnostics (rare)
+        else if (ns > kCand) atomicAdd(counters + 2, 1);
+        else if (counters_on) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 4), (unsigned long long)ns);
       }
     }
   }
@@ -581,7 +643,7 @@ static KnnTcGeom make_tc_geom(const flowb200_params* p) {
 }
 
 struct TcLayout {
-  size_t q16, t16, qinfo, cellinfo, cand, cnt, scratch, fb_list, fb_count, total;
+  size_t q16, t16, qinfo, cellinfo, cand, cnt, fb_list, fb_count, total;
   int grid, fb_cap;
 };
 
@@ -599,7 +661,6 @@ static TcLayout tc_layout(const flowb200_params* p) {
   L.cellinfo = take(ncell * 4 * sizeof(int));
   L.cand = take(n * g.nblk * kCand * sizeof(uint16_t));
   L.cnt = take(n * g.nblk);
-  L.scratch = take((size_t)L.grid * kCollect * kTileM * sizeof(float2));
   L.fb_list = take((size_t)L.fb_cap * 2 * sizeof(int32_t));
   L.fb_count = take(256);
   L.total = off;
@@ -610,7 +671,7 @@ size_t knn_tc_workspace_bytes(const flowb200_params* p) { return tc_layout(p).to
 
 bool knn_tc_supported(const flowb200_params* p) {
   const int T = p->cellw * p->cellh;
-  return T >= 32 && T <= 65535 && (p->k_cell == 5 || p->k_cell == 10 || p->k_cell == 12) && p->k_cell <= 16 &&
+  return T >= 32 && T <= 2048 && (p->k_cell == 5 || p->k_cell == 10 || p->k_cell == 12) && p->k_cell <= 16 &&
          T >= p->k_cell;
 }
 
@@ -626,12 +687,11 @@ static int run_tc(const float* desc_src, const float* desc_tgt, const flowb200_p
   int* cellinfo = reinterpret_cast<int*>(ws + L.cellinfo);
   uint16_t* cand = reinterpret_cast<uint16_t*>(ws + L.cand);
   uint8_t* cnt = reinterpret_cast<uint8_t*>(ws + L.cnt);
-  float2* scratch = reinterpret_cast<float2*>(ws + L.scratch);
   int32_t* fb_list = reinterpret_cast<int32_t*>(ws + L.fb_list);
   int32_t* fb_count = reinterpret_cast<int32_t*>(ws + L.fb_count);
 
   FB_CUDA_CHECK(cudaMemsetAsync(cellinfo, 0, (size_t)ncell * 4 * sizeof(int), stream));
-  FB_CUDA_CHECK(cudaMemsetAsync(fb_count, 0, sizeof(int32_t), stream));
+  FB_CUDA_CHECK(cudaMemsetAsync(fb_count, 0, 8 * sizeof(int32_t), stream));
   knn_prep_query_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(desc_src, (int)n, q16, qinfo);
   FB_LAUNCH_CHECK();
   const size_t tw = (size_t)ncell * g.Tpad;
@@ -642,11 +702,11 @@ static int run_tc(const float* desc_src, const float* desc_tgt, const flowb200_p
   if (!make_map(&mq, q16, (uint64_t)g.W, (uint64_t)g.H, kTileW, kTileH)) return FLOWB200_ECUDA;
   if (!make_map(&mt, t16, (uint64_t)g.Tpad, (uint64_t)ncell, kChunkN, 1)) return FLOWB200_ECUDA;
   const int n_items = ncell * g.tiles_x * g.tiles_y;
-  const size_t smem = (size_t)kTileBytes * (1 + kBStages) + sizeof(SelSmem) + 1024;
+  const size_t smem = (size_t)kTileBytes * (1 + kBStages) + (size_t)kListCap * kTileM * 4 + sizeof(SelSmem) + 1024;
   auto kern = knn_select_kernel<KC>;
   FB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(L.grid, n_items);
-  kern<<<grid, kSelThreads, smem, stream>>>(mq, mt, g, n_items, qinfo, cellinfo, scratch, cand, cnt, dbg_scores);
+  kern<<<grid, kSelThreads, smem, stream>>>(mq, mt, g, n_items, qinfo, cellinfo, cand, cnt, fb_count, stats != nullptr, dbg_scores);
   FB_LAUNCH_CHECK();
 
   const int r = 2 * g.R + 1;
@@ -660,7 +720,8 @@ static int run_tc(const float* desc_src, const float* desc_tgt, const flowb200_p
   if (fsmem > 48 * 1024) FB_CUDA_CHECK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
   fkern<<<4 * kNumSMs, 128, fsmem, stream>>>(desc_src, desc_tgt, g, fb_list, fb_count, L.fb_cap, pvec, lcost, knn_idx);
   FB_LAUNCH_CHECK();
-  if (stats) FB_CUDA_CHECK(cudaMemcpyAsync(stats, fb_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  // stats: {fallback tasks, collect-list overflows, candidate-list overflows, -, sum candidates, sum collected}
+  if (stats) FB_CUDA_CHECK(cudaMemcpyAsync(stats, fb_count, 6 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
   (void)p;
   return FLOWB200_OK;
 }

@@ -76,7 +76,7 @@ def knn_proposals(desc_src, desc_tgt, p: FlowParams, want_idx=False, knn_mode=No
     labels = torch.empty((H, W), dtype=torch.int32, device=dev)
     r = 2 * p.cell_radius + 1
     idx = torch.empty((H, W, r * r, p.k_cell), dtype=torch.int32, device=dev) if want_idx else None
-    stats = torch.zeros(4, dtype=torch.int32, device=dev) if want_idx else None
+    stats = torch.zeros(8, dtype=torch.int32, device=dev) if want_idx else None
     nb = lib.flowb200_knn_workspace_bytes(C.byref(cp))
     ws = _workspace(nb, dev)
     rc = lib.flowb200_knn_proposals(_ptr(desc_src, torch.float32, "desc_src"), _ptr(desc_tgt, torch.float32, "desc_tgt"),

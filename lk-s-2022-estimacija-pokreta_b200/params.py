@@ -9,7 +9,7 @@ neighbours per cell and the number of Gaussian-sampled neighbour proposals grow,
 from dataclasses import dataclass, replace
 
 
-DEFAULT_KNN_MODE = 0          # FLOWB200_KNN_EXACT_FP64 until the tcgen05 prefilter is the default
+DEFAULT_KNN_MODE = 1          # FLOWB200_KNN_TCGEN05 (0 = float64 CUDA-core brute force)
 
 
 @dataclass(frozen=True)

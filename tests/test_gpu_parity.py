@@ -161,7 +161,7 @@ def test_knn_indices_bit_exact(knn_mode, k_cell):
 
 def test_tcgen05_scores_match_fp16_operands():
     """Raw tensor-core ranking scores (TMA + UMMA descriptors + TMEM read-back) against numpy on the same fp16
-    operands: a(q,t) = |t~|^2/2 - q~.t~ with q~, t~ = fp16(64*d), targets in the pos -> pos*s mod T order."""
+    operands: a(q,t) = |q~|^2/2 + |t~|^2/2 - q~.t~ with q~, t~ = fp16(64*d), targets in the pos -> pos*s mod T order."""
     from oracle import daisy as od
     ops = pkg("ops")
     H, W, cw, ch = 40, 48, 12, 10
@@ -197,7 +197,11 @@ def test_tcgen05_scores_match_fp16_operands():
                     px, py = qx0 + (row & 15), qy0 + (row >> 4)
                     if px >= W or py >= H:
                         continue                                  # zero-filled TMA rows
-                    want = nn - t16 @ q16[py, px]
+                    mq = np.float32(0.5 * (q16[py, px] ** 2).sum())
+                    m0 = np.float16(mq).astype(np.float32)
+                    m1 = np.float16(mq - m0).astype(np.float32)
+                    m2 = np.float16(mq - m0 - m1).astype(np.float32)
+                    want = nn - t16 @ q16[py, px] + (np.float64(m0) + m1 + m2)
                     got = scores[item, row, :T]
                     assert np.abs(got - want).max() < 2e-3, (cell, txi, tyi, row, np.abs(got - want).max())
                     assert (scores[item, row, T:] > 5e4).all()    # padding columns can never be selected
