@@ -5,8 +5,8 @@
 // Mapping: one CTA per chain, one thread per label of the current pixel.  All chains of a phase are
 // independent (they read and write only their own pixels), so a phase is one launch; the four phases
 // and the sweeps are stream-ordered.  K-sets (the reference's packedksets cache, daisy i flann.py:256-309)
-// are never materialised: membership L1(v_l, u_k) < tpsi is re-evaluated from the packed vectors held in
-// shared memory.
+// are never materialised: labels are processed in the order of a spatial hash of their flow vectors and
+// membership L1(v_l, u_k) < tpsi is re-evaluated exactly on the 3 x 3 buckets around v_l (see below).
 //
 // Arithmetic modes (include/flowb200.h): float64 with the reference's operation order (bit-exact for any
 // data cost) or int32 in units of 2^-S (bit-exact when lcost == 20*m/2^S).
@@ -53,6 +53,11 @@ struct DpOps<double> {
 };
 
 // lexicographic (value, index) minimum across the warp: lowest index wins ties (np.argmin, :155/:175/:234)
+__device__ __forceinline__ void warp_argmin(int32_t& val, int& idx) {
+  const int m = __reduce_min_sync(0xffffffffu, val);
+  idx = __reduce_min_sync(0xffffffffu, val == m ? idx : 0x7fffffff);
+  val = m;
+}
 template <typename DP>
 __device__ __forceinline__ void warp_argmin(DP& val, int& idx) {
 #pragma unroll
@@ -67,22 +72,168 @@ __device__ __forceinline__ void warp_argmin(DP& val, int& idx) {
 }
 
 // DP = int32_t: CostT = int32_t (m, units of 2^-shift).  DP = double: CostT = float or double (lcost).
-template <typename DP, typename CostT>
-__global__ void __launch_bounds__(512)
+//
+// The K-set S_l = {k : L1(v_l, u_k) < tpsi} is found through a spatial hash instead of a dense K x K scan, and
+// labels that carry the same flow vector are evaluated once.
+//
+// bcd_sort_kernel (once per proposal set; the sets are static across phases and sweeps, which is what the
+// reference's packedksets cache exploits) orders every pixel's labels by (bucket of the flow vector, vector)
+// with bucket edge 2^bshift >= tpsi and 16 x 64 buckets (offset and clamped).  Labels with equal vectors become a
+// contiguous RUN; its first label is the run's LEADER and leaders are numbered 0..D-1 in sorted order.
+//
+// The chain kernel works on runs:
+//   * the pairwise minimum m(l) depends on v_l only, so it is computed once per leader;
+//   * of the previous pixel's labels with equal vector only the one with the smallest (dp, original index)
+//     can be the (lowest-index) minimiser, so each run is represented by that entry;
+//   * the leaders of one bucket are contiguous, so S_l lies in the 3 x 3 bucket ranges around v_l of the
+//     previous pixel's per-leader arrays.
+// The hash only prunes: membership is always decided by the exact L1 test, and ties are resolved to the lowest
+// ORIGINAL label index as in the reference (np.argmin), so labels are bit-identical to the dense evaluation.
+constexpr int kHashY = 16, kHashX = 64, kHashSize = kHashY * kHashX;
+// per-pixel order entry: [0,10) original label, [10,20) leader number of the run, 20 leader, 21 first leader of
+// its bucket, 22 last leader of its bucket, [23,32) run length - 1 (leaders only)
+constexpr uint32_t kOrdLeader = 1u << 20, kOrdBStart = 1u << 21, kOrdBEnd = 1u << 22;
+
+// bucket coordinates are offset and clamped (not wrapped) so that buckets adjacent in x have consecutive keys:
+// the leaders of three x-adjacent buckets form ONE contiguous range.  Clamping merges far-away buckets into the
+// border ones, which is harmless because membership is always decided by the exact L1 test.
+__device__ __forceinline__ int bkt_y(int b) { return min(max(b + kHashY / 2, 0), kHashY - 1); }
+__device__ __forceinline__ int bkt_x(int b) { return min(max(b + kHashX / 2, 0), kHashX - 1); }
+__device__ __forceinline__ int bucket_key(int32_t v, int bshift) {
+  return (bkt_y(vec_dy(v) >> bshift) << 6) | bkt_x(vec_dx(v) >> bshift);
+}
+constexpr uint32_t kRngEmpty = 0x0000FFFFu;   // first = 0xFFFF, last+1 = 0
+
+// stable counting sort of idx_in[0..n) by key(idx) into idx_out (one warp; cnt has nkeys + nkeys/32 entries:
+// counter k lives at k + (k >> 5) so that the per-lane scan of 32 consecutive counters is bank-conflict free)
+__device__ __forceinline__ int cidx(int k) { return k + (k >> 5); }
+
+template <typename KeyFn>
+__device__ __forceinline__ void warp_stable_sort(const uint16_t* idx_in, uint16_t* idx_out, int n, int* cnt, int nkeys,
+                                                 int lane, KeyFn key) {
+  const int per = nkeys >> 5;
+  for (int i = 0; i < per; ++i) cnt[cidx(i * 32 + lane)] = 0;
+  __syncwarp();
+  for (int j = lane; j < n; j += 32) atomicAdd(&cnt[cidx(key(idx_in[j]))], 1);
+  __syncwarp();
+  // exclusive scan of cnt: every lane owns nkeys/32 consecutive counters
+  int sum = 0;
+  for (int i = 0; i < per; ++i) sum += cnt[cidx(lane * per + i)];
+  int pre = sum;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, pre, off);
+    if (lane >= off) pre += t;
+  }
+  pre -= sum;
+  __syncwarp();
+  for (int i = 0; i < per; ++i) {
+    const int c = cnt[cidx(lane * per + i)];
+    cnt[cidx(lane * per + i)] = pre;
+    pre += c;
+  }
+  __syncwarp();
+  // stable scatter, 32 elements at a time in input order
+  for (int j0 = 0; j0 < n; j0 += 32) {
+    const int j = j0 + lane;
+    const bool act = j < n;
+    const int id = act ? idx_in[j] : 0;
+    const int k = act ? key(id) : -1 - lane;        // inactive lanes get unique keys
+    const unsigned same = __match_any_sync(0xffffffffu, k);
+    const int rank = __popc(same & ((1u << lane) - 1));
+    int base = 0;
+    if (act) base = cnt[cidx(k)];
+    __syncwarp();
+    if (act) {
+      idx_out[base + rank] = (uint16_t)id;
+      if (rank == __popc(same) - 1) cnt[cidx(k)] = base + rank + 1;   // last lane of the key group advances the counter
+    }
+    __syncwarp();
+  }
+}
+
+// one warp per pixel
+__global__ void __launch_bounds__(128)
+bcd_sort_kernel(const int32_t* __restrict__ pvec, const int32_t* __restrict__ nprop, int npix, int K, int bshift,
+                uint32_t* __restrict__ order) {
+  __shared__ int cnt_s[4][kHashSize + kHashSize / 32];
+  __shared__ uint16_t idx_s[4][2][512];
+  __shared__ uint16_t lpos_s[4][513];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* cnt = cnt_s[warp];
+  uint16_t* ia = idx_s[warp][0];
+  uint16_t* ib = idx_s[warp][1];
+  uint16_t* lpos = lpos_s[warp];
+  const int fmask = (1 << bshift) - 1;
+  for (int pix = blockIdx.x * 4 + warp; pix < npix; pix += gridDim.x * 4) {
+    const int n = nprop[pix];
+    const int32_t* v = pvec + (size_t)pix * K;
+    uint32_t* o = order + (size_t)pix * K;
+    for (int j = lane; j < n; j += 32) ia[j] = (uint16_t)j;
+    __syncwarp();
+    // LSD: position inside the bucket first, then the bucket
+    const int nfine = max(32, 1 << (2 * bshift));
+    warp_stable_sort(ia, ib, n, cnt, nfine, lane,
+                     [&](int id) { return ((vec_dy(v[id]) & fmask) << bshift) | (vec_dx(v[id]) & fmask); });
+    warp_stable_sort(ib, ia, n, cnt, kHashSize, lane, [&](int id) { return bucket_key(v[id], bshift); });
+    // leaders, leader numbers
+    int nlead = 0;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+      const int j = j0 + lane;
+      bool lead = false;
+      if (j < n) lead = j == 0 || v[ia[j]] != v[ia[j - 1]];
+      const unsigned m = __ballot_sync(0xffffffffu, lead);
+      const int r = nlead + __popc(m & ((1u << lane) - 1));     // leaders before this position
+      if (j < n) {
+        ib[j] = (uint16_t)(lead ? r : r - 1);                   // leader number of the run this position is in
+        if (lead) lpos[r] = (uint16_t)j;
+      }
+      nlead += __popc(m);
+    }
+    if (lane == 0) lpos[nlead] = (uint16_t)n;
+    __syncwarp();
+    for (int j = lane; j < n; j += 32) {
+      const int id = ia[j], r = ib[j];
+      uint32_t e = (uint32_t)id | ((uint32_t)r << 10);
+      if (lpos[r] == j) {
+        e |= kOrdLeader | ((uint32_t)(lpos[r + 1] - j - 1) << 23);
+        const int key = bucket_key(v[id], bshift);
+        if (j == 0 || bucket_key(v[ia[j - 1]], bshift) != key) e |= kOrdBStart;
+        if (r == nlead - 1 || bucket_key(v[ia[lpos[r + 1]]], bshift) != key) e |= kOrdBEnd;
+      }
+      o[j] = e;
+    }
+    __syncwarp();
+  }
+}
+
+template <typename DP> struct RepT;
+template <> struct RepT<int32_t> { using type = unsigned long long; };   // dp << 32 | original label
+template <> struct RepT<double> { using type = double2; };               // (dp, original label)
+
+template <typename DP, typename CostT, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cost, const int32_t* __restrict__ nprop,
-                 int32_t* __restrict__ labels, uint16_t* __restrict__ bp, int H, int W, int K, int Kpad, int phase,
-                 double lamda, int tpsi, int shift) {
+                 const uint32_t* __restrict__ order, int32_t* __restrict__ labels, uint16_t* __restrict__ bp, int H,
+                 int W, int K, int Kpad, int phase, double lamda, int tpsi, int shift, int bshift) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  using Rep = typename RepT<DP>::type;
   const ChainGeom g = chain_geom(phase, blockIdx.x, H, W);
-  const int l = threadIdx.x;
+  const int l = threadIdx.x;                                           // sorted position handled by this thread
   const int nwarps = blockDim.x >> 5;
   const int warp = l >> 5, lane = l & 31;
 
-  DP* dp_s = reinterpret_cast<DP*>(smem_raw);                          // [2][Kpad]
-  DP* red_val = dp_s + 2 * Kpad;                                       // [2][16]
-  int32_t* vec_s = reinterpret_cast<int32_t*>(red_val + 32);           // [2][Kpad]
-  int32_t* red_idx = vec_s + 2 * Kpad;                                 // [2][16]
-  int32_t* oldvec = red_idx + 32;                                      // [len]
+  Rep* rep_s = reinterpret_cast<Rep*>(smem_raw);                        // [2][Kpad] per leader: best (dp, label) of the run
+  DP* dp_s = reinterpret_cast<DP*>(rep_s + 2 * Kpad);                   // [Kpad]    per position (double mode: run scan)
+  DP* m_s = dp_s + Kpad;                                                // [Kpad]    per leader: pairwise minimum
+  DP* red_val = m_s + Kpad;                                             // [2][16]
+  int32_t* vrep_s = reinterpret_cast<int32_t*>(red_val + 32);           // [2][Kpad] per leader: flow vector
+  int32_t* arg_s = vrep_s + 2 * Kpad;                                   // [Kpad]    per leader: back-pointer
+  int32_t* org_s = arg_s + Kpad;                                        // [Kpad]    per position (double mode)
+  int32_t* red_idx = org_s + Kpad;                                      // [2][16]
+  uint32_t* rng_s = reinterpret_cast<uint32_t*>(red_idx + 32);          // [3][kHashSize] first | (last+1) << 16 leader
+  int32_t* oldvec = reinterpret_cast<int32_t*>(rng_s + 3 * kHashSize);  // [len]
+  __shared__ int nlead_s[2];
 
   auto pixel = [&](int i) { return (g.sy + i * g.ystep) * W + (g.sx + i * g.xstep); };
 
@@ -91,49 +242,119 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
     int p = pixel(i);
     oldvec[i] = pvec[(size_t)p * K + labels[p]];
   }
+  for (int i = l; i < 3 * kHashSize; i += blockDim.x) rng_s[i] = kRngEmpty;
   __syncthreads();
 
   const int s = g.ystep + g.xstep;   // +1: image coordinate grows with the step index
   uint16_t* bp_chain = bp + (size_t)blockIdx.x * g.len * Kpad;
   const DP INF = DpOps<DP>::inf();
 
-  // software prefetch of the next pixel's label data
-  int pix = pixel(0);
-  int n_cur = nprop[pix];
-  int32_t v_cur = (l < n_cur) ? pvec[(size_t)pix * K + l] : 0;
-  CostT c_cur = (l < n_cur) ? cost[(size_t)pix * K + l] : CostT(0);
-  int n_prev = 0;
+  // software prefetch of the next two pixels' label data (in sorted order)
+  int n_a = 0, n_b = 0;
+  uint32_t o_a = 0, o_b = 0;
+  int32_t v_a = 0, v_b = 0;
+  CostT c_a = CostT(0), c_b = CostT(0);
+  const ptrdiff_t pstep = (ptrdiff_t)g.ystep * W + g.xstep;        // pixel index increment per chain step
+  const int32_t* f_np = nprop + pixel(0);
+  const uint32_t* f_or = order + (size_t)pixel(0) * K + l;
+  const int32_t* f_pv = pvec + (size_t)pixel(0) * K;
+  const CostT* f_co = cost + (size_t)pixel(0) * K;
+  auto fetch = [&](int i, int& n, uint32_t& o, int32_t& v, CostT& c) {   // must be called with i = 0, 1, 2, ...
+    n = 0; o = 0; v = 0; c = CostT(0);
+    if (i < g.len) {
+      n = *f_np;
+      if (l < n) {
+        o = *f_or;
+        v = f_pv[o & 1023];
+        c = f_co[o & 1023];
+      }
+      f_np += pstep;
+      f_or += pstep * K;
+      f_pv += pstep * K;
+      f_co += pstep * K;
+    }
+  };
+  fetch(0, n_a, o_a, v_a, c_a);
+  fetch(1, n_b, o_b, v_b, c_b);
   DP dpv = INF;
+  int orig = l;
+  int clr_key = -1;                  // bucket this thread opened two steps ago (to be emptied again)
+  int set_key = -1;                  // bucket this thread opened in the previous step
 
   for (int i = 0; i < g.len; ++i) {
-    const int n = n_cur;
-    const int32_t v = v_cur;
-    const CostT c = c_cur;
-    if (i + 1 < g.len) {
-      int pn = pixel(i + 1);
-      n_cur = nprop[pn];
-      v_cur = (l < n_cur) ? pvec[(size_t)pn * K + l] : 0;
-      c_cur = (l < n_cur) ? cost[(size_t)pn * K + l] : CostT(0);
-    }
+    const int n = n_a;
+    const uint32_t of = o_a;
+    const int32_t v = v_a;
+    const CostT c = c_a;
+    n_a = n_b; o_a = o_b; v_a = v_b; c_a = c_b;
+    fetch(i + 2, n_b, o_b, v_b, c_b);
     const int cur = i & 1, prv = cur ^ 1;
-    const int dy = vec_dy(v), dx = vec_dx(v);
+    uint32_t* rng_q = rng_s + ((i + 2) % 3) * kHashSize;   // built at step i-1, queried now
+    uint32_t* rng_b = rng_s + (i % 3) * kHashSize;         // built now, queried at step i+1
+    uint32_t* rng_c = rng_s + ((i + 1) % 3) * kHashSize;   // built at step i-2, queried at i-1: emptied now
+    if (clr_key >= 0) rng_c[clr_key] = kRngEmpty;
+    clr_key = set_key;
+    set_key = -1;
+    orig = (int)(of & 1023);
+    const int run = (int)((of >> 10) & 1023);
+    const bool active = l < n;
 
-    // side terms (sidepsi :84-88): neighbours along the chain axis, old labels; 0 when off-image
-    const int ip = i + s, im = i - s;
-    int psi_p = 0, psi_m = 0;
-    if (ip >= 0 && ip < g.len) psi_p = min(tpsi, l1_vec(dy, dx, oldvec[ip]));
-    if (im >= 0 && im < g.len) psi_m = min(tpsi, l1_vec(dy, dx, oldvec[im]));
+    // ---- phase 1: leaders publish their vector, open their bucket range and reset their run's representative
+    if (active && (of & kOrdLeader)) {
+      vrep_s[cur * Kpad + run] = v;
+      if constexpr (sizeof(DP) == 4) rep_s[cur * Kpad + run] = ~0ull;
+      const int key = bucket_key(v, bshift);
+      uint16_t* half = reinterpret_cast<uint16_t*>(rng_b + key);
+      if (of & kOrdBStart) {
+        half[0] = (uint16_t)run;
+        set_key = key;
+      }
+      if (of & kOrdBEnd) half[1] = (uint16_t)(run + 1);
+    }
+    if (active && l == n - 1) nlead_s[cur] = run + 1;
+    __syncthreads();
 
-    dpv = INF;
-    if (l < n) {
-      if (i == 0) {
-        if constexpr (sizeof(DP) == 8) {   // (psi+ + psi-) + lamda*lcost   (:118-120)
-          dpv = __dadd_rn((double)(psi_p + psi_m), __dmul_rn(lamda, (double)c));
-        } else {
-          dpv = (DP)c + ((psi_p + psi_m) << shift);
+    // ---- phase 2: thread j < D evaluates the pairwise minimum of leader j against the previous pixel's runs
+    if (i > 0 && l < nlead_s[cur]) {
+      const int32_t vq = vrep_s[cur * Kpad + l];
+      const int dy = vec_dy(vq), dx = vec_dx(vq);
+      const int by = dy >> bshift, bx = dx >> bshift;
+      DP best = INF;
+      int arg = 0x7fffffff;
+      const Rep* rp = rep_s + prv * Kpad;
+      const int32_t* vp = vrep_s + prv * Kpad;
+      const int kx0 = bkt_x(bx - 1), kx1 = bkt_x(bx), kx2 = bkt_x(bx + 1);
+#pragma unroll 1
+      for (int oy = -1; oy <= 1; ++oy) {
+        // the three x-adjacent buckets of this bucket row are one contiguous leader range
+        const uint32_t* row = rng_q + (bkt_y(by + oy) << 6);
+        const uint32_t r0 = row[kx0], r1 = row[kx1], r2 = row[kx2];
+        const int t0 = (int)min(min(r0 & 0xFFFFu, r1 & 0xFFFFu), r2 & 0xFFFFu);
+        const int t1 = (int)max(max(r0 >> 16, r1 >> 16), r2 >> 16);
+#pragma unroll 2
+        for (int t = t0; t < t1; ++t) {
+          const int l1 = l1_vec(dy, dx, vp[t]);
+          if (l1 < tpsi) {          // near candidates (the K-set, :131-142; :170-175 / :213-218)
+            DP cand;
+            int k;
+            if constexpr (sizeof(DP) == 8) {
+              const double2 r = rp[t];
+              cand = __dadd_rn(r.x, (double)l1);
+              k = (int)r.y;
+            } else {
+              const unsigned long long r = rp[t];
+              cand = (DP)(r >> 32) + (l1 << shift);
+              k = (int)(r & 0xffffffffu);
+            }
+            if (cand < best || (cand == best && k < arg)) {   // np.argmin: lowest k wins ties
+              best = cand;
+              arg = k;
+            }
+          }
         }
-      } else {
-        // truncation candidate: min_k (tpsi + dp_prev[k]), lowest k (:152-157)
+      }
+      if (arg == 0x7fffffff) {            // quirk Q1: truncation only when the K-set is empty
+        // min_k (tpsi + dp_prev[k]), lowest k (:152-157)
         DP tr = red_val[prv * 16];
         int tr_arg = red_idx[prv * 16];
         for (int w = 1; w < nwarps; ++w) {
@@ -144,61 +365,85 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
             tr_arg = oi;
           }
         }
-        // near candidates: k with L1(v_l, u_k) < tpsi  (the K-set, :131-142; :170-175 / :213-218)
-        DP best = INF;
-        int arg = 0;
-        const DP* dpp = dp_s + prv * Kpad;
-        const int32_t* vp = vec_s + prv * Kpad;
-#pragma unroll 4
-        for (int k = 0; k < n_prev; ++k) {
-          int l1 = l1_vec(dy, dx, vp[k]);
-          DP cand;
-          if constexpr (sizeof(DP) == 8) {
-            cand = __dadd_rn(dpp[k], (double)l1);
-          } else {
-            cand = dpp[k] + (l1 << shift);
-          }
-          if (l1 < tpsi && cand < best) {   // strict <: lowest k wins ties
-            best = cand;
-            arg = k;
-          }
+        best = tr;
+        arg = tr_arg;
+      }
+      m_s[l] = best;
+      arg_s[l] = arg;
+    }
+    if (i > 0) __syncthreads();
+
+    // ---- phase 3: every label adds its own unary term; runs elect their representative
+    dpv = INF;
+    if (active) {
+      const int dy = vec_dy(v), dx = vec_dx(v);
+      // side terms (sidepsi :84-88): neighbours along the chain axis, old labels; 0 when off-image
+      const int ip = i + s, im = i - s;
+      int psi_p = 0, psi_m = 0;
+      if (ip >= 0 && ip < g.len) psi_p = min(tpsi, l1_vec(dy, dx, oldvec[ip]));
+      if (im >= 0 && im < g.len) psi_m = min(tpsi, l1_vec(dy, dx, oldvec[im]));
+      if (i == 0) {
+        if constexpr (sizeof(DP) == 8) {   // (psi+ + psi-) + lamda*lcost   (:118-120)
+          dpv = __dadd_rn((double)(psi_p + psi_m), __dmul_rn(lamda, (double)c));
+        } else {
+          dpv = (DP)c + ((psi_p + psi_m) << shift);
         }
-        DP m = best;
-        if (!(best < INF)) {                // quirk Q1: truncation only when the K-set is empty
-          m = tr;
-          arg = tr_arg;
-        }
+      } else {
+        const DP m = m_s[run];
         if constexpr (sizeof(DP) == 8) {    // (lamda*lcost + psi+) + psi-, then m + that  (:161-162, :176)
           double U = __dadd_rn(__dadd_rn(__dmul_rn(lamda, (double)c), (double)psi_p), (double)psi_m);
           dpv = __dadd_rn(m, U);
         } else {
           dpv = m + (DP)c + ((psi_p + psi_m) << shift);
         }
-        bp_chain[(size_t)i * Kpad + l] = (uint16_t)arg;
+        bp_chain[(size_t)i * Kpad + orig] = (uint16_t)arg_s[run];
       }
-      dp_s[cur * Kpad + l] = dpv;
-      vec_s[cur * Kpad + l] = v;
+      if constexpr (sizeof(DP) == 4) {
+        const unsigned long long key = ((unsigned long long)(uint32_t)dpv << 32) | (uint32_t)orig;
+        if ((of & kOrdLeader) && (of >> 23) == 0) rep_s[cur * Kpad + run] = key;      // run of one label
+        else atomicMin(rep_s + cur * Kpad + run, key);
+      } else {
+        dp_s[l] = dpv;
+        org_s[l] = orig;
+      }
     }
-    // block argmin of (tpsi + dp) for the next step
+    // block argmin of (tpsi + dp) for the next step's truncation candidate, ties -> lowest original index
     DP rv = INF;
-    if (l < n) {
+    if (active) {
       if constexpr (sizeof(DP) == 8) rv = __dadd_rn((double)tpsi, dpv);
       else rv = dpv + (tpsi << shift);
     }
-    int ri = l;
+    int ri = active ? orig : 0x7fffffff;
     warp_argmin(rv, ri);
     if (lane == 0) {
       red_val[cur * 16 + warp] = rv;
       red_idx[cur * 16 + warp] = ri;
     }
-    n_prev = n;
+    if constexpr (sizeof(DP) == 8) {
+      // float64 mode (parity / arbitrary costs): the leader scans its run for the representative
+      __syncthreads();
+      if (active && (of & kOrdLeader)) {
+        const int len = (int)(of >> 23) + 1;
+        double bd = dpv;
+        int bo = orig;
+        for (int t = 1; t < len; ++t) {
+          const double od = dp_s[l + t];
+          const int oo = org_s[l + t];
+          if (od < bd || (od == bd && oo < bo)) {
+            bd = od;
+            bo = oo;
+          }
+        }
+        rep_s[cur * Kpad + run] = make_double2(bd, (double)bo);
+      }
+    }
     __syncthreads();
   }
 
   // final label: lowest-index argmin of dp_last (:231-237), then backtrack (:238-253)
   {
-    DP rv = dpv;   // INF for l >= n
-    int ri = l;
+    DP rv = dpv;   // INF for inactive threads
+    int ri = (rv < INF) ? orig : 0x7fffffff;
     warp_argmin(rv, ri);
     const int fin = g.len & 1;   // buffer not used by the last step's reduction (cur = (len-1)&1)
     if (lane == 0) {
@@ -228,17 +473,28 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
 template <typename DP, typename CostT>
 static int launch_sweeps(const int32_t* pvec, const CostT* cost, const int32_t* nprop, int32_t* labels, int H, int W,
                          int K, double lamda, int tpsi, int shift, int sweeps, int32_t* labels_per_sweep, uint16_t* bp,
-                         cudaStream_t stream) {
+                         uint32_t* order, cudaStream_t stream) {
   const int Kpad = (K + 31) / 32 * 32;
-  auto kern = bcd_chain_kernel<DP, CostT>;
+  const bool small = Kpad <= 320;
+  auto kern = small ? bcd_chain_kernel<DP, CostT, 320, (sizeof(DP) == 4 ? 4 : 2)> : bcd_chain_kernel<DP, CostT, 512, 1>;
   const int maxlen = H > W ? H : W;
-  size_t smem = 2 * (size_t)Kpad * (sizeof(DP) + 4) + 32 * (sizeof(DP) + 4) + (size_t)maxlen * 4;
-  if (smem > 48 * 1024) FB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  size_t smem = (size_t)Kpad * (2 * sizeof(typename RepT<DP>::type) + 2 * sizeof(DP) + 16) + 32 * (sizeof(DP) + 4) +
+                3 * (size_t)kHashSize * 4 + (size_t)maxlen * 4;
+  FB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int bshift = 0;
+  while ((1 << bshift) < tpsi) ++bshift;
+  if (bshift > 5) return FLOWB200_EUNSUPPORTED;
+  if (sweeps > 0) {
+    const int npix = H * W;
+    bcd_sort_kernel<<<min((npix + 3) / 4, 16 * kNumSMs), 128, 0, stream>>>(pvec, nprop, npix, K, bshift, order);
+    FB_LAUNCH_CHECK();
+  }
   for (int w = 0; w < sweeps; ++w) {
     for (int phase = 0; phase < 4; ++phase) {
       int nch = phase_chains(phase, H, W);
       if (nch == 0) continue;
-      kern<<<nch, Kpad, smem, stream>>>(pvec, cost, nprop, labels, bp, H, W, K, Kpad, phase, lamda, tpsi, shift);
+      kern<<<nch, Kpad, smem, stream>>>(pvec, cost, nprop, order, labels, bp, H, W, K, Kpad, phase, lamda, tpsi, shift,
+                                        bshift);
       FB_LAUNCH_CHECK();
     }
     if (labels_per_sweep)
@@ -264,7 +520,7 @@ extern "C" size_t flowb200_bcd_workspace_bytes(int H, int W, int K) {
   if (H <= 0 || W <= 0 || K <= 0) return 0;
   size_t Kpad = (size_t)(K + 31) / 32 * 32;
   size_t col = (size_t)((W + 1) / 2) * H, row = (size_t)((H + 1) / 2) * W;
-  return align_up((col > row ? col : row) * Kpad * sizeof(uint16_t));
+  return align_up((col > row ? col : row) * Kpad * sizeof(uint16_t)) + align_up((size_t)H * W * K * sizeof(uint32_t));
 }
 
 extern "C" int flowb200_bcd(const int32_t* pvec, const void* cost, const int32_t* nprop, int32_t* labels, int H, int W,
@@ -276,17 +532,24 @@ extern "C" int flowb200_bcd(const int32_t* pvec, const void* cost, const int32_t
   if (H > 16384 || W > 16384) return FLOWB200_EINVAL;
   if (workspace_bytes < flowb200_bcd_workspace_bytes(H, W, K)) return FLOWB200_EWORKSPACE;
   uint16_t* bp = static_cast<uint16_t*>(workspace);
+  uint32_t* order;
+  {
+    size_t Kpad = (size_t)(K + 31) / 32 * 32;
+    size_t col = (size_t)((W + 1) / 2) * H, row = (size_t)((H + 1) / 2) * W;
+    order = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) +
+                                        align_up((col > row ? col : row) * Kpad * sizeof(uint16_t)));
+  }
   switch (bcd_mode) {
     case FLOWB200_BCD_FP64_F32COST:
       return launch_sweeps<double, float>(pvec, static_cast<const float*>(cost), nprop, labels, H, W, K, lamda, tpsi, 0,
-                                          sweeps, labels_per_sweep, bp, stream);
+                                          sweeps, labels_per_sweep, bp, order, stream);
     case FLOWB200_BCD_FP64_F64COST:
       return launch_sweeps<double, double>(pvec, static_cast<const double*>(cost), nprop, labels, H, W, K, lamda, tpsi,
-                                           0, sweeps, labels_per_sweep, bp, stream);
+                                           0, sweeps, labels_per_sweep, bp, order, stream);
     case FLOWB200_BCD_INT32:
       if (cost_shift < 0 || cost_shift > 14) return FLOWB200_EINVAL;
       return launch_sweeps<int32_t, int32_t>(pvec, static_cast<const int32_t*>(cost), nprop, labels, H, W, K, lamda,
-                                             tpsi, cost_shift, sweeps, labels_per_sweep, bp, stream);
+                                             tpsi, cost_shift, sweeps, labels_per_sweep, bp, order, stream);
     default:
       return FLOWB200_EINVAL;
   }

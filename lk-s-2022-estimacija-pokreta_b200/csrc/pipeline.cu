@@ -18,6 +18,27 @@ void set_cuda_error(cudaError_t e, const char* where) {
 static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// one auxiliary stream (+ fork/join events) per device and host thread, created on first use
+struct AuxStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static AuxStream* aux_stream() {
+  static thread_local AuxStream table[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  AuxStream* a = &table[dev];
+  if (!a->stream) {
+    if (cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&a->fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&a->join, cudaEventDisableTiming) != cudaSuccess) {
+      a->stream = nullptr;
+      return nullptr;
+    }
+  }
+  return a;
+}
+
 struct PairLayout {
   size_t desc[2], daisy_ws, pvec[2], lcost[2], mcost[2], nprop[2], labels[2], uvv[2], bcd_ws[2], knn_ws[2], total;
 };
@@ -119,8 +140,23 @@ extern "C" int flowb200_flow_pair(const uint8_t* bgr0, const uint8_t* bgr1, cons
   if (rc) return rc;
   rc = flowb200_daisy(bgr1, p->H, p->W, reinterpret_cast<float*>(ws + L.desc[1]), ws + L.daisy_ws, dws, stream);
   if (rc) return rc;
-  for (int d = 0; d < directions; ++d) {
-    rc = run_direction(p, L, ws, d, sweeps, seed, stream);
+  // forward and backward are independent (README.md:40): the backward direction runs on an auxiliary stream
+  // so that the small launches of one direction (BCD row phases have only H/2 chains) fill the SMs the other
+  // leaves idle.  fork: aux waits for the DAISYs; join: `stream` waits for aux before the consistency check.
+  AuxStream* aux = directions == 2 ? aux_stream() : nullptr;
+  if (aux) {
+    FB_CUDA_CHECK(cudaEventRecord(aux->fork, stream));
+    FB_CUDA_CHECK(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
+    rc = run_direction(p, L, ws, 1, sweeps, seed, aux->stream);
+    if (rc) return rc;
+    FB_CUDA_CHECK(cudaEventRecord(aux->join, aux->stream));
+  }
+  rc = run_direction(p, L, ws, 0, sweeps, seed, stream);
+  if (rc) return rc;
+  if (aux) {
+    FB_CUDA_CHECK(cudaStreamWaitEvent(stream, aux->join, 0));
+  } else if (directions == 2) {
+    rc = run_direction(p, L, ws, 1, sweeps, seed, stream);
     if (rc) return rc;
   }
   const size_t fbytes = n * 3 * sizeof(float);
