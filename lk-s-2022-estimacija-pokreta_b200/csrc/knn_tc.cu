@@ -427,7 +427,7 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
-// 3. exact re-rank + data cost.  16 lanes per (query, cell) task, lane = candidate.
+// 3. exact re-rank + data cost.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double exact_dist(const float* __restrict__ q, const float* __restrict__ t) {
   double acc = 0.0;
@@ -459,72 +459,148 @@ __device__ __forceinline__ void emit_proposal(const KnnTcGeom& g, const float* _
   if (knn_idx) knn_idx[(pix * g.nblk + blk) * KC + rank] = idx;
 }
 
+// One pass over a (query, target) descriptor pair:
+//   ds   float32 screening distance, sum of fl(q-t)^2 with FMA.  All terms are >= 0, so it is within a relative
+//        70 * 2^-24 = 4.2e-6 of the real-valued distance (and the float64 oracle value within 1e-14 of it);
+//   cost the float32 L1 data cost sum |fl(q-t)| in numpy's pairwise order (daisy i flann.py:178-180), exactly as
+//        sum68_numpy_order evaluates it.
+__device__ __forceinline__ void screen_and_cost(const float* __restrict__ q, const float* __restrict__ t, float& ds,
+                                                float& cost) {
+  float acc = 0.f, r[8], tail[4];
+#pragma unroll
+  for (int d = 0; d < kDescDim; d += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(q + d);     // same 272 B for the whole half-warp: L1 hits
+    const float4 b = *reinterpret_cast<const float4*>(t + d);
+    const float e[4] = {__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z), __fsub_rn(a.w, b.w)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc = fmaf(e[i], e[i], acc);
+      const float ae = fabsf(e[i]);
+      if (d + i < 8) r[d + i] = ae;
+      else if (d + i < 64) r[(d + i) & 7] = __fadd_rn(r[(d + i) & 7], ae);
+      else tail[d + i - 64] = ae;
+    }
+  }
+  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) res = __fadd_rn(res, tail[i]);
+  ds = acc;
+  cost = res;
+}
+
+__device__ __noinline__ double exact_dist_call(const float* __restrict__ q, const float* __restrict__ t) {
+  return exact_dist(q, t);
+}
+
+// One half-warp per source pixel, looping over the pixel's cells (= blocks of the slot order); lane = candidate.
+// Ranking uses the float32 screening distance wherever it decides the order with certainty (relative gap > 2e-5);
+// candidates involved in an uncertain pair get the exact float64 distance of the oracle, so the final order is
+// always the oracle's (distance, index) order.
 template <int KC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 knn_rerank_kernel(const float* __restrict__ desc_src, const float* __restrict__ desc_tgt, KnnTcGeom g,
                   const uint16_t* __restrict__ cand, const uint8_t* __restrict__ cand_cnt, int32_t* __restrict__ pvec,
                   float* __restrict__ lcost, int32_t* __restrict__ knn_idx, int32_t* __restrict__ fb_list,
                   int32_t* __restrict__ fb_count, int fb_cap) {
-  // grid: (query groups of the band, cells); 16 tasks per block of 256 threads
-  const int cell = blockIdx.y;
-  const int ci = cell % g.ncellx, cj = cell / g.ncellx;
-  const int x0 = max(0, g.cellw * (ci - g.R)), x1 = min(g.W, g.cellw * (ci + g.R + 1));
-  const int y0 = max(0, g.cellh * (cj - g.R)), y1 = min(g.H, g.cellh * (cj + g.R + 1));
-  const int bw = x1 - x0, nq = bw * (y1 - y0);
   const int sub = threadIdx.x & 15;
-  const int qi = blockIdx.x * 16 + (threadIdx.x >> 4);
-  if (qi >= nq) return;
-  const int qy = y0 + qi / bw, qx = x0 + qi % bw;
+  const size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  if (pix >= (size_t)g.H * g.W) return;
+  const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);
+  const int qy = (int)(pix / g.W), qx = (int)(pix - (size_t)qy * g.W);
   int cimin, cimax, cjmin, cjmax;
   cell_range(qx, g.cellw, g.ncellx, g.R, &cimin, &cimax);
   cell_range(qy, g.cellh, g.ncelly, g.R, &cjmin, &cjmax);
-  const int blk = (ci - cimin) * (cjmax - cjmin + 1) + (cj - cjmin);
-  const size_t pix = (size_t)qy * g.W + qx;
-  const size_t task = pix * g.nblk + blk;
-  const int n = cand_cnt[task];
-  const unsigned gmask = 0xFFFFu << (threadIdx.x & 16);
-  if (n == 255) {
-    if (sub == 0) {
-      const int at = atomicAdd(fb_count, 1);
-      if (at < fb_cap) {
-        fb_list[2 * at] = (int)pix;
-        fb_list[2 * at + 1] = cell;
+  const float* qp = desc_src + pix * kDescDim;
+  int blk = 0;
+  for (int ci = cimin; ci <= cimax; ++ci) {
+    for (int cj = cjmin; cj <= cjmax; ++cj, ++blk) {
+      const size_t task = pix * g.nblk + blk;
+      const int n = cand_cnt[task];
+      if (n == 255) {
+        if (sub == 0) {
+          const int at = atomicAdd(fb_count, 1);
+          if (at < fb_cap) {
+            fb_list[2 * at] = (int)pix;
+            fb_list[2 * at + 1] = ci + cj * g.ncellx;
+          }
+        }
+        continue;
       }
-    }
-    return;
-  }
-  const float* q = desc_src + pix * kDescDim;
-  const int ty0 = cj * g.cellh, tx0 = ci * g.cellw;
-  // two rounds of 16 candidates
-  double d[2];
-  int id[2];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int c = h * 16 + sub;
-    d[h] = CUDART_INF;
-    id[h] = 0x7fffffff;
-    if (c < n) {
-      id[h] = cand[task * kCand + c];
-      const int r = id[h] / g.cellw, cc = id[h] - r * g.cellw;
-      d[h] = exact_dist(q, desc_tgt + ((size_t)(ty0 + r) * g.W + tx0 + cc) * kDescDim);
-    }
-    if (n <= 16) break;
-  }
-  // rank = number of candidates that precede (d, id) lexicographically
-  const int rounds = n <= 16 ? 1 : 2;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    if (h >= rounds) break;
-    int rank = 0;
-    for (int o = 0; o < rounds; ++o) {
+      const int ty0 = cj * g.cellh, tx0 = ci * g.cellw;
+      // candidates 0..15 in round 0, 16..31 in round 1 (rare: only when more than 16 survived the prefilter)
+      float ds0 = CUDART_INF_F, ds1 = CUDART_INF_F, co0 = 0.f, co1 = 0.f;
+      int id0 = 0x7fffffff, id1 = 0x7fffffff;
+      const float* tp0 = nullptr;
+      const float* tp1 = nullptr;
+      if (sub < n) {
+        id0 = cand[task * kCand + sub];
+        const int r = id0 / g.cellw, cc = id0 - r * g.cellw;
+        tp0 = desc_tgt + ((size_t)(ty0 + r) * g.W + tx0 + cc) * kDescDim;
+        screen_and_cost(qp, tp0, ds0, co0);
+      }
+      const bool two = n > 16;
+      if (two && 16 + sub < n) {
+        id1 = cand[task * kCand + 16 + sub];
+        const int r = id1 / g.cellw, cc = id1 - r * g.cellw;
+        tp1 = desc_tgt + ((size_t)(ty0 + r) * g.W + tx0 + cc) * kDescDim;
+        screen_and_cost(qp, tp1, ds1, co1);
+      }
+      // rank by the screening distance; note every pair it cannot order with certainty
+      const float lo0 = ds0 * (1.0f - 1.0e-5f), hi0 = ds0 * (1.0f + 1.0e-5f);
+      const float lo1 = ds1 * (1.0f - 1.0e-5f), hi1 = ds1 * (1.0f + 1.0e-5f);
+      int rank0 = 0, rank1 = 0;
+      bool amb0 = false, amb1 = false;
       for (int l = 0; l < 16; ++l) {
-        const double od = __shfl_sync(gmask, d[o], l, 16);
-        const int oi = __shfl_sync(gmask, id[o], l, 16);
-        rank += (od < d[h] || (od == d[h] && oi < id[h])) ? 1 : 0;
+        const float od = __shfl_sync(gmask, ds0, l, 16);
+        const float ol = od * (1.0f - 1.0e-5f), oh = od * (1.0f + 1.0e-5f);
+        rank0 += od < ds0;
+        amb0 |= (l != sub) && !(oh < lo0) && !(hi0 < ol);
+        rank1 += od < ds1;
+        amb1 |= !(oh < lo1) && !(hi1 < ol);
+      }
+      if (two) {
+        for (int l = 0; l < 16; ++l) {
+          const float od = __shfl_sync(gmask, ds1, l, 16);
+          const float ol = od * (1.0f - 1.0e-5f), oh = od * (1.0f + 1.0e-5f);
+          rank0 += od < ds0;
+          amb0 |= !(oh < lo0) && !(hi0 < ol);
+          rank1 += od < ds1;
+          amb1 |= (l != sub) && !(oh < lo1) && !(hi1 < ol);
+        }
+      }
+      amb0 &= ds0 < CUDART_INF_F;      // (inf is "certainly larger" than every finite distance: hi < inf)
+      amb1 &= ds1 < CUDART_INF_F;
+      if (__any_sync(gmask, amb0 || amb1)) {
+        // exact float64 distances for the uncertain candidates, then the oracle's (distance, index) order
+        double dx0 = 0.0, dx1 = 0.0;
+        if (amb0) dx0 = exact_dist_call(qp, tp0);
+        if (amb1) dx1 = exact_dist_call(qp, tp1);
+        rank0 = rank1 = 0;
+        for (int o = 0; o < (two ? 2 : 1); ++o)
+          for (int l = 0; l < 16; ++l) {
+            const float od = __shfl_sync(gmask, o ? ds1 : ds0, l, 16);
+            const int oi = __shfl_sync(gmask, o ? id1 : id0, l, 16);
+            const bool oa = __shfl_sync(gmask, (int)(o ? amb1 : amb0), l, 16) != 0;
+            const double ox = __shfl_sync(gmask, o ? dx1 : dx0, l, 16);
+            rank0 += ((oa && amb0) ? (ox < dx0 || (ox == dx0 && oi < id0)) : (od < ds0)) ? 1 : 0;
+            rank1 += ((oa && amb1) ? (ox < dx1 || (ox == dx1 && oi < id1)) : (od < ds1)) ? 1 : 0;
+          }
+      }
+      const size_t obase = pix * g.K + (size_t)KC * blk;
+      if (sub < n && rank0 < KC) {
+        const int r = id0 / g.cellw, cc = id0 - r * g.cellw;
+        pvec[obase + rank0] = pack_vec(ty0 + r - qy, tx0 + cc - qx);
+        lcost[obase + rank0] = co0 < g.tphi ? co0 : g.tphi;       // min(tphi, sum) (:178-180)
+        if (knn_idx) knn_idx[(pix * g.nblk + blk) * KC + rank0] = id0;
+      }
+      if (two && 16 + sub < n && rank1 < KC) {
+        const int r = id1 / g.cellw, cc = id1 - r * g.cellw;
+        pvec[obase + rank1] = pack_vec(ty0 + r - qy, tx0 + cc - qx);
+        lcost[obase + rank1] = co1 < g.tphi ? co1 : g.tphi;
+        if (knn_idx) knn_idx[(pix * g.nblk + blk) * KC + rank1] = id1;
       }
     }
-    if (h * 16 + sub < n && rank < KC)
-      emit_proposal<KC>(g, q, desc_tgt, qx, qy, ci, cj, blk, rank, id[h], pvec, lcost, knn_idx);
   }
 }
 
@@ -709,9 +785,7 @@ static int run_tc(const float* desc_src, const float* desc_tgt, const flowb200_p
   kern<<<grid, kSelThreads, smem, stream>>>(mq, mt, g, n_items, qinfo, cellinfo, cand, cnt, fb_count, stats != nullptr, dbg_scores);
   FB_LAUNCH_CHECK();
 
-  const int r = 2 * g.R + 1;
-  const int maxq = min(g.W, r * g.cellw) * min(g.H, r * g.cellh);
-  dim3 rgrid((maxq + 15) / 16, ncell);
+  const unsigned rgrid = (unsigned)((n * 16 + 255) / 256);
   knn_rerank_kernel<KC><<<rgrid, 256, 0, stream>>>(desc_src, desc_tgt, g, cand, cnt, pvec, lcost, knn_idx, fb_list,
                                                     fb_count, L.fb_cap);
   FB_LAUNCH_CHECK();
