@@ -206,7 +206,7 @@ __device__ __forceinline__ bool decode_item(const KnnTcGeom& g, int item, int& c
   return qx0 < x1 && qy0 < y1;
 }
 
-template <int KC>
+template <int KC, bool DBG>
 __global__ void __launch_bounds__(kSelThreads, 2)
 knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t, KnnTcGeom g,
                   int n_items, const float2* __restrict__ qinfo, const int* __restrict__ cellinfo,
@@ -250,13 +250,13 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int cell, qx0, qy0, x1, y1;
         if (!decode_item(g, item, cell, qx0, qy0, x1, y1)) continue;
-        ptx::mbar_wait_backoff(&ss->a_empty, (it & 1) ^ 1, 64);
+        ptx::mbar_wait_backoff(&ss->a_empty, (it & 1) ^ 1, 2000);
         ptx::mbar_arrive_expect_tx(&ss->a_full, kTileBytes);
 #pragma unroll
         for (int kb = 0; kb < kKB; ++kb) ptx::tma_load_3d(sA + kb * kSlabBytes, &tmap_q, &ss->a_full, kb * 16, qx0, qy0);
         for (int c = 0; c < nchunks; ++c, ++bcount) {
           const uint32_t st = bcount % kBStages, ph = (bcount / kBStages) & 1;
-          ptx::mbar_wait_backoff(&ss->b_empty[st], ph ^ 1, 64);
+          ptx::mbar_wait_backoff(&ss->b_empty[st], ph ^ 1, 2000);
           ptx::mbar_arrive_expect_tx(&ss->b_full[st], kTileBytes);
 #pragma unroll
           for (int kb = 0; kb < kKB; ++kb)
@@ -273,12 +273,12 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         int cell, qx0, qy0, x1, y1;
         if (!decode_item(g, item, cell, qx0, qy0, x1, y1)) continue;
-        ptx::mbar_wait_backoff(&ss->a_full, it & 1, 32);
+        ptx::mbar_wait_backoff(&ss->a_full, it & 1, 1000);
         for (int c = 0; c < nchunks; ++c, ++bcount) {
           const uint32_t st = bcount % kBStages, ph = (bcount / kBStages) & 1;
           const uint32_t acc = bcount % kAccStages, aph = (bcount / kAccStages) & 1;
-          ptx::mbar_wait_backoff(&ss->b_full[st], ph, 32);
-          ptx::mbar_wait_backoff(&ss->t_empty[acc], aph ^ 1, 32);
+          ptx::mbar_wait_backoff(&ss->b_full[st], ph, 1000);
+          ptx::mbar_wait_backoff(&ss->t_empty[acc], aph ^ 1, 1000);
           ptx::tc_fence_after();
 #pragma unroll
           for (int kb = 0; kb < kKB; ++kb) {
@@ -323,7 +323,7 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       // so the truncated score is <= the score: later filters on the stored value keep a superset).
       uint32_t waddr = list_base;               // shared address of the next free entry of this row
       auto process = [&](const uint32_t (&r)[32], int pos0, bool first) {
-        if (dbg_scores) {
+        if constexpr (DBG) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             dbg_scores[((size_t)item * kTileM + row) * g.Tpad + pos0 + j] = __uint_as_float(r[j]);
@@ -373,7 +373,7 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
       for (int c = 0; c < nchunks; ++c, ++bcount) {
         const uint32_t acc = bcount % kAccStages, aph = (bcount / kAccStages) & 1;
-        ptx::mbar_wait_backoff(&ss->t_full[acc], aph, 20);
+        ptx::mbar_wait_backoff(&ss->t_full[acc], aph, 500);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kChunkN;
         const int cpos = c * kChunkN;
@@ -779,7 +779,7 @@ static int run_tc(const float* desc_src, const float* desc_tgt, const flowb200_p
   if (!make_map(&mt, t16, (uint64_t)g.Tpad, (uint64_t)ncell, kChunkN, 1)) return FLOWB200_ECUDA;
   const int n_items = ncell * g.tiles_x * g.tiles_y;
   const size_t smem = (size_t)kTileBytes * (1 + kBStages) + (size_t)kListCap * kTileM * 4 + sizeof(SelSmem) + 1024;
-  auto kern = knn_select_kernel<KC>;
+  auto kern = dbg_scores ? knn_select_kernel<KC, true> : knn_select_kernel<KC, false>;
   FB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(L.grid, n_items);
   kern<<<grid, kSelThreads, smem, stream>>>(mq, mt, g, n_items, qinfo, cellinfo, cand, cnt, fb_count, stats != nullptr, dbg_scores);

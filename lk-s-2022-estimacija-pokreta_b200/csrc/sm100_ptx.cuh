@@ -50,21 +50,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-// same, but sleeps between probes so that a waiting single-thread role does not steal issue slots
+// same, but lets the hardware suspend the thread for up to `ns` nanoseconds per probe, so that a waiting
+// single-thread role does not steal issue slots from the warps doing the work
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
   for (;;) {
     uint32_t done;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
         : "memory");
     if (done) break;
-    __nanosleep(ns);
   }
 }
 
