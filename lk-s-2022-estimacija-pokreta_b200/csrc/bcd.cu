@@ -278,8 +278,29 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
   fetch(1, n_b, o_b, v_b, c_b);
   DP dpv = INF;
   int orig = l;
-  int clr_key = -1;                  // bucket this thread opened two steps ago (to be emptied again)
-  int set_key = -1;                  // bucket this thread opened in the previous step
+  int key0 = -1, key1 = -1, key2 = -1;   // buckets this thread opened 0 / 1 / 2 builds ago (emptied after their query)
+
+  // Leaders of pixel `i` publish their flow vector, open their bucket's leader range and reset their run's
+  // representative.  Runs one step ahead (from the prefetched registers), so it needs no barrier of its own.
+  auto publish = [&](int i, int n, uint32_t of, int32_t v) {
+    const int buf = i & 1;
+    uint32_t* rng_b = rng_s + (i % 3) * kHashSize;
+    if (l < n && (of & kOrdLeader)) {
+      const int run = (int)((of >> 10) & 1023);
+      vrep_s[buf * Kpad + run] = v;
+      if constexpr (sizeof(DP) == 4) rep_s[buf * Kpad + run] = ~0ull;
+      const int key = bucket_key(v, bshift);
+      uint16_t* half = reinterpret_cast<uint16_t*>(rng_b + key);
+      if (of & kOrdBStart) {
+        half[0] = (uint16_t)run;
+        key0 = key;
+      }
+      if (of & kOrdBEnd) half[1] = (uint16_t)(run + 1);
+    }
+    if (l < n && l == n - 1) nlead_s[buf] = (int)((of >> 10) & 1023) + 1;
+  };
+  publish(0, n_a, o_a, v_a);
+  __syncthreads();
 
   for (int i = 0; i < g.len; ++i) {
     const int n = n_a;
@@ -289,30 +310,16 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
     n_a = n_b; o_a = o_b; v_a = v_b; c_a = c_b;
     fetch(i + 2, n_b, o_b, v_b, c_b);
     const int cur = i & 1, prv = cur ^ 1;
-    uint32_t* rng_q = rng_s + ((i + 2) % 3) * kHashSize;   // built at step i-1, queried now
-    uint32_t* rng_b = rng_s + (i % 3) * kHashSize;         // built now, queried at step i+1
-    uint32_t* rng_c = rng_s + ((i + 1) % 3) * kHashSize;   // built at step i-2, queried at i-1: emptied now
-    if (clr_key >= 0) rng_c[clr_key] = kRngEmpty;
-    clr_key = set_key;
-    set_key = -1;
+    uint32_t* rng_q = rng_s + ((i + 2) % 3) * kHashSize;   // ranges of pixel i-1, queried now
+    uint32_t* rng_c = rng_s + ((i + 1) % 3) * kHashSize;   // ranges of pixel i-2 (queried at step i-1): emptied now,
+                                                           // refilled for pixel i+1 after this step's first barrier
+    if (key2 >= 0) rng_c[key2] = kRngEmpty;
+    key2 = key1;
+    key1 = key0;
+    key0 = -1;
     orig = (int)(of & 1023);
     const int run = (int)((of >> 10) & 1023);
     const bool active = l < n;
-
-    // ---- phase 1: leaders publish their vector, open their bucket range and reset their run's representative
-    if (active && (of & kOrdLeader)) {
-      vrep_s[cur * Kpad + run] = v;
-      if constexpr (sizeof(DP) == 4) rep_s[cur * Kpad + run] = ~0ull;
-      const int key = bucket_key(v, bshift);
-      uint16_t* half = reinterpret_cast<uint16_t*>(rng_b + key);
-      if (of & kOrdBStart) {
-        half[0] = (uint16_t)run;
-        set_key = key;
-      }
-      if (of & kOrdBEnd) half[1] = (uint16_t)(run + 1);
-    }
-    if (active && l == n - 1) nlead_s[cur] = run + 1;
-    __syncthreads();
 
     // ---- phase 2: thread j < D evaluates the pairwise minimum of leader j against the previous pixel's runs
     if (i > 0 && l < nlead_s[cur]) {
@@ -321,6 +328,8 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
       const int by = dy >> bshift, bx = dx >> bshift;
       DP best = INF;
       int arg = 0x7fffffff;
+      unsigned long long key_a = ~0ull, key_b = ~0ull, key_c = ~0ull, key_d = ~0ull;
+      (void)key_a; (void)key_b; (void)key_c; (void)key_d;
       const Rep* rp = rep_s + prv * Kpad;
       const int32_t* vp = vrep_s + prv * Kpad;
       const int kx0 = bkt_x(bx - 1), kx1 = bkt_x(bx), kx2 = bkt_x(bx + 1);
@@ -331,26 +340,49 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
         const uint32_t r0 = row[kx0], r1 = row[kx1], r2 = row[kx2];
         const int t0 = (int)min(min(r0 & 0xFFFFu, r1 & 0xFFFFu), r2 & 0xFFFFu);
         const int t1 = (int)max(max(r0 >> 16, r1 >> 16), r2 >> 16);
-#pragma unroll 2
-        for (int t = t0; t < t1; ++t) {
-          const int l1 = l1_vec(dy, dx, vp[t]);
-          if (l1 < tpsi) {          // near candidates (the K-set, :131-142; :170-175 / :213-218)
-            DP cand;
-            int k;
-            if constexpr (sizeof(DP) == 8) {
+        if constexpr (sizeof(DP) == 4) {
+          // int32 mode: (dp << 32 | label) keys make "lowest label wins ties" a plain 64-bit minimum; four
+          // independent accumulators keep four candidates in flight
+          int t = t0;
+          for (; t + 3 < t1; t += 4) {
+            const int32_t ua = vp[t], ub = vp[t + 1], uc = vp[t + 2], ud = vp[t + 3];
+            const unsigned long long ra = rp[t], rb = rp[t + 1], rc = rp[t + 2], rd = rp[t + 3];
+            const int la = l1_vec(dy, dx, ua), lb = l1_vec(dy, dx, ub), lc = l1_vec(dy, dx, uc), ld = l1_vec(dy, dx, ud);
+            const unsigned long long ka = ra + ((unsigned long long)(uint32_t)(la << shift) << 32);
+            const unsigned long long kb = rb + ((unsigned long long)(uint32_t)(lb << shift) << 32);
+            const unsigned long long kc = rc + ((unsigned long long)(uint32_t)(lc << shift) << 32);
+            const unsigned long long kd = rd + ((unsigned long long)(uint32_t)(ld << shift) << 32);
+            if (la < tpsi && ka < key_a) key_a = ka;      // near candidates (the K-set, :131-142; :170-175 / :213-218)
+            if (lb < tpsi && kb < key_b) key_b = kb;
+            if (lc < tpsi && kc < key_c) key_c = kc;
+            if (ld < tpsi && kd < key_d) key_d = kd;
+          }
+          for (; t < t1; ++t) {
+            const int la = l1_vec(dy, dx, vp[t]);
+            const unsigned long long ka = rp[t] + ((unsigned long long)(uint32_t)(la << shift) << 32);
+            if (la < tpsi && ka < key_a) key_a = ka;
+          }
+        } else {
+          for (int t = t0; t < t1; ++t) {
+            const int l1 = l1_vec(dy, dx, vp[t]);
+            if (l1 < tpsi) {
               const double2 r = rp[t];
-              cand = __dadd_rn(r.x, (double)l1);
-              k = (int)r.y;
-            } else {
-              const unsigned long long r = rp[t];
-              cand = (DP)(r >> 32) + (l1 << shift);
-              k = (int)(r & 0xffffffffu);
-            }
-            if (cand < best || (cand == best && k < arg)) {   // np.argmin: lowest k wins ties
-              best = cand;
-              arg = k;
+              const double cand = __dadd_rn(r.x, (double)l1);
+              const int k = (int)r.y;
+              if (cand < best || (cand == best && k < arg)) {   // np.argmin: lowest k wins ties
+                best = cand;
+                arg = k;
+              }
             }
           }
+        }
+      }
+      if constexpr (sizeof(DP) == 4) {
+        const unsigned long long kab = key_a < key_b ? key_a : key_b, kcd = key_c < key_d ? key_c : key_d;
+        const unsigned long long kk = kab < kcd ? kab : kcd;
+        if (kk != ~0ull) {
+          best = (DP)(kk >> 32);
+          arg = (int)(kk & 0xffffffffu);
         }
       }
       if (arg == 0x7fffffff) {            // quirk Q1: truncation only when the K-set is empty
@@ -407,6 +439,7 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
         org_s[l] = orig;
       }
     }
+    if (i + 1 < g.len) publish(i + 1, n_a, o_a, v_a);
     // block argmin of (tpsi + dp) for the next step's truncation candidate, ties -> lowest original index
     DP rv = INF;
     if (active) {
