@@ -2,7 +2,7 @@
 // Reference: `python bcd.py` bcd() :101-257 (one chain), ceoBCD() :261-284 (phase order),
 // sidepsi :84-88, purepsi :98-99.  See oracle/bcd.py for the recurrence in words.
 //
-// Mapping: one CTA per chain, one thread per label of the current pixel.  All chains of a phase are
+// Mapping: one CTA of 128 threads per chain, a few labels of the current pixel per thread.  All chains of a phase are
 // independent (they read and write only their own pixels), so a phase is one launch; the four phases
 // and the sweeps are stream-ordered.  K-sets (the reference's packedksets cache, daisy i flann.py:256-309)
 // are never materialised: labels are processed in the order of a spatial hash of their flow vectors and
@@ -211,16 +211,19 @@ template <typename DP> struct RepT;
 template <> struct RepT<int32_t> { using type = unsigned long long; };   // dp << 32 | original label
 template <> struct RepT<double> { using type = double2; };               // (dp, original label)
 
-template <typename DP, typename CostT, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
+// One CTA of T threads per chain; thread l handles the sorted positions l, l+T, ... (PER of them).  Few warps per
+// chain keep the two barriers of a step cheap and let one thread average over several labels (the per-step time
+// is set by the slowest thread), while all chains of a phase -- and both directions -- are resident at once.
+template <typename DP, typename CostT, int T, int PER, int MINB>
+__global__ void __launch_bounds__(T, MINB)
 bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cost, const int32_t* __restrict__ nprop,
                  const uint32_t* __restrict__ order, int32_t* __restrict__ labels, uint16_t* __restrict__ bp, int H,
                  int W, int K, int Kpad, int phase, double lamda, int tpsi, int shift, int bshift) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using Rep = typename RepT<DP>::type;
+  constexpr int NW = T / 32;
   const ChainGeom g = chain_geom(phase, blockIdx.x, H, W);
-  const int l = threadIdx.x;                                           // sorted position handled by this thread
-  const int nwarps = blockDim.x >> 5;
+  const int l = threadIdx.x;
   const int warp = l >> 5, lane = l & 31;
 
   Rep* rep_s = reinterpret_cast<Rep*>(smem_raw);                        // [2][Kpad] per leader: best (dp, label) of the run
@@ -238,11 +241,11 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
   auto pixel = [&](int i) { return (g.sy + i * g.ystep) * W + (g.sx + i * g.xstep); };
 
   // vectors of the chain's labels before this call (bestlabels is only rewritten by the backtrack)
-  for (int i = l; i < g.len; i += blockDim.x) {
+  for (int i = l; i < g.len; i += T) {
     int p = pixel(i);
     oldvec[i] = pvec[(size_t)p * K + labels[p]];
   }
-  for (int i = l; i < 3 * kHashSize; i += blockDim.x) rng_s[i] = kRngEmpty;
+  for (int i = l; i < 3 * kHashSize; i += T) rng_s[i] = kRngEmpty;
   __syncthreads();
 
   const int s = g.ystep + g.xstep;   // +1: image coordinate grows with the step index
@@ -251,23 +254,29 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
 
   // software prefetch of the next two pixels' label data (in sorted order)
   int n_a = 0, n_b = 0;
-  uint32_t o_a = 0, o_b = 0;
-  int32_t v_a = 0, v_b = 0;
-  CostT c_a = CostT(0), c_b = CostT(0);
+  uint32_t o_a[PER], o_b[PER];
+  int32_t v_a[PER], v_b[PER];
+  CostT c_a[PER], c_b[PER];
   const ptrdiff_t pstep = (ptrdiff_t)g.ystep * W + g.xstep;        // pixel index increment per chain step
   const int32_t* f_np = nprop + pixel(0);
   const uint32_t* f_or = order + (size_t)pixel(0) * K + l;
   const int32_t* f_pv = pvec + (size_t)pixel(0) * K;
   const CostT* f_co = cost + (size_t)pixel(0) * K;
-  auto fetch = [&](int i, int& n, uint32_t& o, int32_t& v, CostT& c) {   // must be called with i = 0, 1, 2, ...
-    n = 0; o = 0; v = 0; c = CostT(0);
+  auto fetch = [&](int i, int& n, uint32_t (&o)[PER], int32_t (&v)[PER], CostT (&c)[PER]) {   // i = 0, 1, 2, ...
+    n = 0;
+#pragma unroll
+    for (int r = 0; r < PER; ++r) { o[r] = 0; v[r] = 0; c[r] = CostT(0); }
     if (i < g.len) {
       n = *f_np;
-      if (l < n) {
-        o = *f_or;
-        v = f_pv[o & 1023];
-        c = f_co[o & 1023];
-      }
+#pragma unroll
+      for (int r = 0; r < PER; ++r)
+        if (l + r * T < n) o[r] = f_or[r * T];
+#pragma unroll
+      for (int r = 0; r < PER; ++r)
+        if (l + r * T < n) {
+          v[r] = f_pv[o[r] & 1023];
+          c[r] = f_co[o[r] & 1023];
+        }
       f_np += pstep;
       f_or += pstep * K;
       f_pv += pstep * K;
@@ -276,177 +285,203 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
   };
   fetch(0, n_a, o_a, v_a, c_a);
   fetch(1, n_b, o_b, v_b, c_b);
-  DP dpv = INF;
-  int orig = l;
-  int key0 = -1, key1 = -1, key2 = -1;   // buckets this thread opened 0 / 1 / 2 builds ago (emptied after their query)
+  DP dpv[PER];
+  int orig[PER];
+  int key0[PER], key1[PER], key2[PER];   // buckets opened 0 / 1 / 2 builds ago (emptied after their query)
+#pragma unroll
+  for (int r = 0; r < PER; ++r) { dpv[r] = INF; orig[r] = 0; key0[r] = key1[r] = key2[r] = -1; }
 
   // Leaders of pixel `i` publish their flow vector, open their bucket's leader range and reset their run's
   // representative.  Runs one step ahead (from the prefetched registers), so it needs no barrier of its own.
-  auto publish = [&](int i, int n, uint32_t of, int32_t v) {
+  auto publish = [&](int i, int n, const uint32_t (&of)[PER], const int32_t (&v)[PER]) {
     const int buf = i & 1;
     uint32_t* rng_b = rng_s + (i % 3) * kHashSize;
-    if (l < n && (of & kOrdLeader)) {
-      const int run = (int)((of >> 10) & 1023);
-      vrep_s[buf * Kpad + run] = v;
-      if constexpr (sizeof(DP) == 4) rep_s[buf * Kpad + run] = ~0ull;
-      const int key = bucket_key(v, bshift);
-      uint16_t* half = reinterpret_cast<uint16_t*>(rng_b + key);
-      if (of & kOrdBStart) {
-        half[0] = (uint16_t)run;
-        key0 = key;
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+      const int p = l + r * T;
+      if (p < n && (of[r] & kOrdLeader)) {
+        const int run = (int)((of[r] >> 10) & 1023);
+        vrep_s[buf * Kpad + run] = v[r];
+        if constexpr (sizeof(DP) == 4) rep_s[buf * Kpad + run] = ~0ull;
+        const int key = bucket_key(v[r], bshift);
+        uint16_t* half = reinterpret_cast<uint16_t*>(rng_b + key);
+        if (of[r] & kOrdBStart) {
+          half[0] = (uint16_t)run;
+          key0[r] = key;
+        }
+        if (of[r] & kOrdBEnd) half[1] = (uint16_t)(run + 1);
       }
-      if (of & kOrdBEnd) half[1] = (uint16_t)(run + 1);
+      if (p < n && p == n - 1) nlead_s[buf] = (int)((of[r] >> 10) & 1023) + 1;
     }
-    if (l < n && l == n - 1) nlead_s[buf] = (int)((of >> 10) & 1023) + 1;
   };
   publish(0, n_a, o_a, v_a);
   __syncthreads();
 
   for (int i = 0; i < g.len; ++i) {
     const int n = n_a;
-    const uint32_t of = o_a;
-    const int32_t v = v_a;
-    const CostT c = c_a;
-    n_a = n_b; o_a = o_b; v_a = v_b; c_a = c_b;
+    uint32_t of[PER];
+    int32_t v[PER];
+    CostT c[PER];
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+      of[r] = o_a[r]; v[r] = v_a[r]; c[r] = c_a[r];
+      o_a[r] = o_b[r]; v_a[r] = v_b[r]; c_a[r] = c_b[r];
+    }
+    n_a = n_b;
     fetch(i + 2, n_b, o_b, v_b, c_b);
     const int cur = i & 1, prv = cur ^ 1;
     uint32_t* rng_q = rng_s + ((i + 2) % 3) * kHashSize;   // ranges of pixel i-1, queried now
     uint32_t* rng_c = rng_s + ((i + 1) % 3) * kHashSize;   // ranges of pixel i-2 (queried at step i-1): emptied now,
                                                            // refilled for pixel i+1 after this step's first barrier
-    if (key2 >= 0) rng_c[key2] = kRngEmpty;
-    key2 = key1;
-    key1 = key0;
-    key0 = -1;
-    orig = (int)(of & 1023);
-    const int run = (int)((of >> 10) & 1023);
-    const bool active = l < n;
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+      if (key2[r] >= 0) rng_c[key2[r]] = kRngEmpty;
+      key2[r] = key1[r];
+      key1[r] = key0[r];
+      key0[r] = -1;
+      orig[r] = (int)(of[r] & 1023);
+    }
 
-    // ---- phase 2: thread j < D evaluates the pairwise minimum of leader j against the previous pixel's runs
-    if (i > 0 && l < nlead_s[cur]) {
-      const int32_t vq = vrep_s[cur * Kpad + l];
-      const int dy = vec_dy(vq), dx = vec_dx(vq);
-      const int by = dy >> bshift, bx = dx >> bshift;
-      DP best = INF;
-      int arg = 0x7fffffff;
-      unsigned long long key_a = ~0ull, key_b = ~0ull, key_c = ~0ull, key_d = ~0ull;
-      (void)key_a; (void)key_b; (void)key_c; (void)key_d;
+    // ---- phase 2: leader j's pairwise minimum against the previous pixel's runs (threads take leaders j, j+T, ..)
+    if (i > 0) {
+      const int D = nlead_s[cur];
       const Rep* rp = rep_s + prv * Kpad;
       const int32_t* vp = vrep_s + prv * Kpad;
-      const int kx0 = bkt_x(bx - 1), kx1 = bkt_x(bx), kx2 = bkt_x(bx + 1);
 #pragma unroll 1
-      for (int oy = -1; oy <= 1; ++oy) {
-        // the three x-adjacent buckets of this bucket row are one contiguous leader range
-        const uint32_t* row = rng_q + (bkt_y(by + oy) << 6);
-        const uint32_t r0 = row[kx0], r1 = row[kx1], r2 = row[kx2];
-        const int t0 = (int)min(min(r0 & 0xFFFFu, r1 & 0xFFFFu), r2 & 0xFFFFu);
-        const int t1 = (int)max(max(r0 >> 16, r1 >> 16), r2 >> 16);
-        if constexpr (sizeof(DP) == 4) {
-          // int32 mode: (dp << 32 | label) keys make "lowest label wins ties" a plain 64-bit minimum; four
-          // independent accumulators keep four candidates in flight
-          int t = t0;
-          for (; t + 3 < t1; t += 4) {
-            const int32_t ua = vp[t], ub = vp[t + 1], uc = vp[t + 2], ud = vp[t + 3];
-            const unsigned long long ra = rp[t], rb = rp[t + 1], rc = rp[t + 2], rd = rp[t + 3];
-            const int la = l1_vec(dy, dx, ua), lb = l1_vec(dy, dx, ub), lc = l1_vec(dy, dx, uc), ld = l1_vec(dy, dx, ud);
-            const unsigned long long ka = ra + ((unsigned long long)(uint32_t)(la << shift) << 32);
-            const unsigned long long kb = rb + ((unsigned long long)(uint32_t)(lb << shift) << 32);
-            const unsigned long long kc = rc + ((unsigned long long)(uint32_t)(lc << shift) << 32);
-            const unsigned long long kd = rd + ((unsigned long long)(uint32_t)(ld << shift) << 32);
-            if (la < tpsi && ka < key_a) key_a = ka;      // near candidates (the K-set, :131-142; :170-175 / :213-218)
-            if (lb < tpsi && kb < key_b) key_b = kb;
-            if (lc < tpsi && kc < key_c) key_c = kc;
-            if (ld < tpsi && kd < key_d) key_d = kd;
-          }
-          for (; t < t1; ++t) {
-            const int la = l1_vec(dy, dx, vp[t]);
-            const unsigned long long ka = rp[t] + ((unsigned long long)(uint32_t)(la << shift) << 32);
-            if (la < tpsi && ka < key_a) key_a = ka;
-          }
-        } else {
-          for (int t = t0; t < t1; ++t) {
-            const int l1 = l1_vec(dy, dx, vp[t]);
-            if (l1 < tpsi) {
-              const double2 r = rp[t];
-              const double cand = __dadd_rn(r.x, (double)l1);
-              const int k = (int)r.y;
-              if (cand < best || (cand == best && k < arg)) {   // np.argmin: lowest k wins ties
-                best = cand;
-                arg = k;
+      for (int L = l; L < D; L += T) {
+        const int32_t vq = vrep_s[cur * Kpad + L];
+        const int dy = vec_dy(vq), dx = vec_dx(vq);
+        const int by = dy >> bshift, bx = dx >> bshift;
+        DP best = INF;
+        int arg = 0x7fffffff;
+        unsigned long long key_a = ~0ull, key_b = ~0ull, key_c = ~0ull, key_d = ~0ull;
+        (void)key_a; (void)key_b; (void)key_c; (void)key_d;
+        const int kx0 = bkt_x(bx - 1), kx1 = bkt_x(bx), kx2 = bkt_x(bx + 1);
+#pragma unroll 1
+        for (int oy = -1; oy <= 1; ++oy) {
+          // the three x-adjacent buckets of this bucket row are one contiguous leader range
+          const uint32_t* row = rng_q + (bkt_y(by + oy) << 6);
+          const uint32_t r0 = row[kx0], r1 = row[kx1], r2 = row[kx2];
+          const int t0 = (int)min(min(r0 & 0xFFFFu, r1 & 0xFFFFu), r2 & 0xFFFFu);
+          const int t1 = (int)max(max(r0 >> 16, r1 >> 16), r2 >> 16);
+          if constexpr (sizeof(DP) == 4) {
+            // int32 mode: (dp << 32 | label) keys make "lowest label wins ties" a plain 64-bit minimum; four
+            // independent accumulators keep four candidates in flight
+            int t = t0;
+            for (; t + 3 < t1; t += 4) {
+              const int32_t ua = vp[t], ub = vp[t + 1], uc = vp[t + 2], ud = vp[t + 3];
+              const unsigned long long ra = rp[t], rb = rp[t + 1], rc = rp[t + 2], rd = rp[t + 3];
+              const int la = l1_vec(dy, dx, ua), lb = l1_vec(dy, dx, ub), lc = l1_vec(dy, dx, uc),
+                        ld = l1_vec(dy, dx, ud);
+              const unsigned long long ka = ra + ((unsigned long long)(uint32_t)(la << shift) << 32);
+              const unsigned long long kb = rb + ((unsigned long long)(uint32_t)(lb << shift) << 32);
+              const unsigned long long kc = rc + ((unsigned long long)(uint32_t)(lc << shift) << 32);
+              const unsigned long long kd = rd + ((unsigned long long)(uint32_t)(ld << shift) << 32);
+              if (la < tpsi && ka < key_a) key_a = ka;    // near candidates (the K-set, :131-142; :170-175 / :213-218)
+              if (lb < tpsi && kb < key_b) key_b = kb;
+              if (lc < tpsi && kc < key_c) key_c = kc;
+              if (ld < tpsi && kd < key_d) key_d = kd;
+            }
+            for (; t < t1; ++t) {
+              const int la = l1_vec(dy, dx, vp[t]);
+              const unsigned long long ka = rp[t] + ((unsigned long long)(uint32_t)(la << shift) << 32);
+              if (la < tpsi && ka < key_a) key_a = ka;
+            }
+          } else {
+            for (int t = t0; t < t1; ++t) {
+              const int l1 = l1_vec(dy, dx, vp[t]);
+              if (l1 < tpsi) {
+                const double2 r = rp[t];
+                const double cand = __dadd_rn(r.x, (double)l1);
+                const int k = (int)r.y;
+                if (cand < best || (cand == best && k < arg)) {   // np.argmin: lowest k wins ties
+                  best = cand;
+                  arg = k;
+                }
               }
             }
           }
         }
-      }
-      if constexpr (sizeof(DP) == 4) {
-        const unsigned long long kab = key_a < key_b ? key_a : key_b, kcd = key_c < key_d ? key_c : key_d;
-        const unsigned long long kk = kab < kcd ? kab : kcd;
-        if (kk != ~0ull) {
-          best = (DP)(kk >> 32);
-          arg = (int)(kk & 0xffffffffu);
-        }
-      }
-      if (arg == 0x7fffffff) {            // quirk Q1: truncation only when the K-set is empty
-        // min_k (tpsi + dp_prev[k]), lowest k (:152-157)
-        DP tr = red_val[prv * 16];
-        int tr_arg = red_idx[prv * 16];
-        for (int w = 1; w < nwarps; ++w) {
-          DP ov = red_val[prv * 16 + w];
-          int oi = red_idx[prv * 16 + w];
-          if (ov < tr || (ov == tr && oi < tr_arg)) {
-            tr = ov;
-            tr_arg = oi;
+        if constexpr (sizeof(DP) == 4) {
+          const unsigned long long kab = key_a < key_b ? key_a : key_b, kcd = key_c < key_d ? key_c : key_d;
+          const unsigned long long kk = kab < kcd ? kab : kcd;
+          if (kk != ~0ull) {
+            best = (DP)(kk >> 32);
+            arg = (int)(kk & 0xffffffffu);
           }
         }
-        best = tr;
-        arg = tr_arg;
+        if (arg == 0x7fffffff) {            // quirk Q1: truncation only when the K-set is empty
+          // min_k (tpsi + dp_prev[k]), lowest k (:152-157)
+          DP tr = red_val[prv * 16];
+          int tr_arg = red_idx[prv * 16];
+#pragma unroll
+          for (int w = 1; w < NW; ++w) {
+            DP ov = red_val[prv * 16 + w];
+            int oi = red_idx[prv * 16 + w];
+            if (ov < tr || (ov == tr && oi < tr_arg)) {
+              tr = ov;
+              tr_arg = oi;
+            }
+          }
+          best = tr;
+          arg = tr_arg;
+        }
+        m_s[L] = best;
+        arg_s[L] = arg;
       }
-      m_s[l] = best;
-      arg_s[l] = arg;
+      __syncthreads();
     }
-    if (i > 0) __syncthreads();
 
     // ---- phase 3: every label adds its own unary term; runs elect their representative
-    dpv = INF;
-    if (active) {
-      const int dy = vec_dy(v), dx = vec_dx(v);
-      // side terms (sidepsi :84-88): neighbours along the chain axis, old labels; 0 when off-image
-      const int ip = i + s, im = i - s;
-      int psi_p = 0, psi_m = 0;
-      if (ip >= 0 && ip < g.len) psi_p = min(tpsi, l1_vec(dy, dx, oldvec[ip]));
-      if (im >= 0 && im < g.len) psi_m = min(tpsi, l1_vec(dy, dx, oldvec[im]));
-      if (i == 0) {
-        if constexpr (sizeof(DP) == 8) {   // (psi+ + psi-) + lamda*lcost   (:118-120)
-          dpv = __dadd_rn((double)(psi_p + psi_m), __dmul_rn(lamda, (double)c));
+    DP rv = INF;                       // running (tpsi + dp, label) minimum over this thread's labels
+    int ri = 0x7fffffff;
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+      const int p = l + r * T;
+      dpv[r] = INF;
+      if (p < n) {
+        const int run = (int)((of[r] >> 10) & 1023);
+        const int dy = vec_dy(v[r]), dx = vec_dx(v[r]);
+        // side terms (sidepsi :84-88): neighbours along the chain axis, old labels; 0 when off-image
+        const int ip = i + s, im = i - s;
+        int psi_p = 0, psi_m = 0;
+        if (ip >= 0 && ip < g.len) psi_p = min(tpsi, l1_vec(dy, dx, oldvec[ip]));
+        if (im >= 0 && im < g.len) psi_m = min(tpsi, l1_vec(dy, dx, oldvec[im]));
+        if (i == 0) {
+          if constexpr (sizeof(DP) == 8) {   // (psi+ + psi-) + lamda*lcost   (:118-120)
+            dpv[r] = __dadd_rn((double)(psi_p + psi_m), __dmul_rn(lamda, (double)c[r]));
+          } else {
+            dpv[r] = (DP)c[r] + ((psi_p + psi_m) << shift);
+          }
         } else {
-          dpv = (DP)c + ((psi_p + psi_m) << shift);
+          const DP m = m_s[run];
+          if constexpr (sizeof(DP) == 8) {    // (lamda*lcost + psi+) + psi-, then m + that  (:161-162, :176)
+            double U = __dadd_rn(__dadd_rn(__dmul_rn(lamda, (double)c[r]), (double)psi_p), (double)psi_m);
+            dpv[r] = __dadd_rn(m, U);
+          } else {
+            dpv[r] = m + (DP)c[r] + ((psi_p + psi_m) << shift);
+          }
+          bp_chain[(size_t)i * Kpad + orig[r]] = (uint16_t)arg_s[run];
         }
-      } else {
-        const DP m = m_s[run];
-        if constexpr (sizeof(DP) == 8) {    // (lamda*lcost + psi+) + psi-, then m + that  (:161-162, :176)
-          double U = __dadd_rn(__dadd_rn(__dmul_rn(lamda, (double)c), (double)psi_p), (double)psi_m);
-          dpv = __dadd_rn(m, U);
+        if constexpr (sizeof(DP) == 4) {
+          const unsigned long long key = ((unsigned long long)(uint32_t)dpv[r] << 32) | (uint32_t)orig[r];
+          if ((of[r] & kOrdLeader) && (of[r] >> 23) == 0) rep_s[cur * Kpad + run] = key;      // run of one label
+          else atomicMin(rep_s + cur * Kpad + run, key);
         } else {
-          dpv = m + (DP)c + ((psi_p + psi_m) << shift);
+          dp_s[p] = dpv[r];
+          org_s[p] = orig[r];
         }
-        bp_chain[(size_t)i * Kpad + orig] = (uint16_t)arg_s[run];
-      }
-      if constexpr (sizeof(DP) == 4) {
-        const unsigned long long key = ((unsigned long long)(uint32_t)dpv << 32) | (uint32_t)orig;
-        if ((of & kOrdLeader) && (of >> 23) == 0) rep_s[cur * Kpad + run] = key;      // run of one label
-        else atomicMin(rep_s + cur * Kpad + run, key);
-      } else {
-        dp_s[l] = dpv;
-        org_s[l] = orig;
+        DP tv;
+        if constexpr (sizeof(DP) == 8) tv = __dadd_rn((double)tpsi, dpv[r]);
+        else tv = dpv[r] + (tpsi << shift);
+        if (tv < rv || (tv == rv && orig[r] < ri)) {
+          rv = tv;
+          ri = orig[r];
+        }
       }
     }
     if (i + 1 < g.len) publish(i + 1, n_a, o_a, v_a);
     // block argmin of (tpsi + dp) for the next step's truncation candidate, ties -> lowest original index
-    DP rv = INF;
-    if (active) {
-      if constexpr (sizeof(DP) == 8) rv = __dadd_rn((double)tpsi, dpv);
-      else rv = dpv + (tpsi << shift);
-    }
-    int ri = active ? orig : 0x7fffffff;
     warp_argmin(rv, ri);
     if (lane == 0) {
       red_val[cur * 16 + warp] = rv;
@@ -455,19 +490,24 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
     if constexpr (sizeof(DP) == 8) {
       // float64 mode (parity / arbitrary costs): the leader scans its run for the representative
       __syncthreads();
-      if (active && (of & kOrdLeader)) {
-        const int len = (int)(of >> 23) + 1;
-        double bd = dpv;
-        int bo = orig;
-        for (int t = 1; t < len; ++t) {
-          const double od = dp_s[l + t];
-          const int oo = org_s[l + t];
-          if (od < bd || (od == bd && oo < bo)) {
-            bd = od;
-            bo = oo;
+#pragma unroll
+      for (int r = 0; r < PER; ++r) {
+        const int p = l + r * T;
+        if (p < n && (of[r] & kOrdLeader)) {
+          const int run = (int)((of[r] >> 10) & 1023);
+          const int len = (int)(of[r] >> 23) + 1;
+          double bd = dpv[r];
+          int bo = orig[r];
+          for (int t = 1; t < len; ++t) {
+            const double od = dp_s[p + t];
+            const int oo = org_s[p + t];
+            if (od < bd || (od == bd && oo < bo)) {
+              bd = od;
+              bo = oo;
+            }
           }
+          rep_s[cur * Kpad + run] = make_double2(bd, (double)bo);
         }
-        rep_s[cur * Kpad + run] = make_double2(bd, (double)bo);
       }
     }
     __syncthreads();
@@ -475,8 +515,15 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
 
   // final label: lowest-index argmin of dp_last (:231-237), then backtrack (:238-253)
   {
-    DP rv = dpv;   // INF for inactive threads
-    int ri = (rv < INF) ? orig : 0x7fffffff;
+    DP rv = INF;
+    int ri = 0x7fffffff;
+#pragma unroll
+    for (int r = 0; r < PER; ++r)
+      if (dpv[r] < rv || (dpv[r] == rv && dpv[r] < INF && orig[r] < ri)) {
+        rv = dpv[r];
+        ri = orig[r];
+      }
+    if (!(rv < INF)) ri = 0x7fffffff;
     warp_argmin(rv, ri);
     const int fin = g.len & 1;   // buffer not used by the last step's reduction (cur = (len-1)&1)
     if (lane == 0) {
@@ -487,7 +534,7 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
     if (l == 0) {
       DP bv = red_val[fin * 16];
       int lab = red_idx[fin * 16];
-      for (int w = 1; w < nwarps; ++w) {
+      for (int w = 1; w < NW; ++w) {
         DP ov = red_val[fin * 16 + w];
         int oi = red_idx[fin * 16 + w];
         if (ov < bv || (ov == bv && oi < lab)) {
@@ -508,8 +555,13 @@ static int launch_sweeps(const int32_t* pvec, const CostT* cost, const int32_t* 
                          int K, double lamda, int tpsi, int shift, int sweeps, int32_t* labels_per_sweep, uint16_t* bp,
                          uint32_t* order, cudaStream_t stream) {
   const int Kpad = (K + 31) / 32 * 32;
-  const bool small = Kpad <= 320;
-  auto kern = small ? bcd_chain_kernel<DP, CostT, 320, (sizeof(DP) == 4 ? 4 : 2)> : bcd_chain_kernel<DP, CostT, 512, 1>;
+  constexpr int T = 128;
+  void (*kern)(const int32_t*, const CostT*, const int32_t*, const uint32_t*, int32_t*, uint16_t*, int, int, int, int,
+               int, double, int, int, int);
+  if (K <= T) kern = bcd_chain_kernel<DP, CostT, T, 1, 4>;
+  else if (K <= 2 * T) kern = bcd_chain_kernel<DP, CostT, T, 2, 4>;
+  else if (K <= 3 * T) kern = bcd_chain_kernel<DP, CostT, T, 3, 4>;
+  else kern = bcd_chain_kernel<DP, CostT, T, 4, 3>;
   const int maxlen = H > W ? H : W;
   size_t smem = (size_t)Kpad * (2 * sizeof(typename RepT<DP>::type) + 2 * sizeof(DP) + 16) + 32 * (sizeof(DP) + 4) +
                 3 * (size_t)kHashSize * 4 + (size_t)maxlen * 4;
@@ -526,8 +578,8 @@ static int launch_sweeps(const int32_t* pvec, const CostT* cost, const int32_t* 
     for (int phase = 0; phase < 4; ++phase) {
       int nch = phase_chains(phase, H, W);
       if (nch == 0) continue;
-      kern<<<nch, Kpad, smem, stream>>>(pvec, cost, nprop, order, labels, bp, H, W, K, Kpad, phase, lamda, tpsi, shift,
-                                        bshift);
+      kern<<<nch, T, smem, stream>>>(pvec, cost, nprop, order, labels, bp, H, W, K, Kpad, phase, lamda, tpsi, shift,
+                                     bshift);
       FB_LAUNCH_CHECK();
     }
     if (labels_per_sweep)
