@@ -6,8 +6,10 @@
 // result is bit-identical to the oracle, not merely within 1e-4.
 //
 // Layout: the four orientation layers of a pixel are one float4, so every blur tap and every petal
-// tap is a single 16-byte access; the descriptor write (272 B/pixel) is the HBM-bound part and is
-// issued as fully coalesced float4 stores (one thread per (pixel, region)).
+// tap is a single 16-byte access.  Seven launches per image: gray + pre-blur + gradient + layers fused in one
+// shared-memory tile kernel; every separable blur does both passes in one kernel through shared memory; the
+// sampler stages the four cubes of a 32 x 8 tile (+halo) in shared memory and writes the descriptor
+// (272 B/pixel, the HBM-bound part) as fully coalesced float4 stores.
 #include "common.cuh"
 #include "daisy_constants.h"
 
@@ -23,14 +25,6 @@ struct GridPts {
   int cube[17];
 };
 
-__global__ void gray_kernel(const uint8_t* __restrict__ bgr, float* __restrict__ gray, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int b = bgr[3 * (size_t)i], g = bgr[3 * (size_t)i + 1], r = bgr[3 * (size_t)i + 2];
-  int y = (b * 3735 + g * 19235 + r * 9798 + 16384) >> 15;     // cv2 BGR2GRAY, 15-bit fixed point
-  gray[i] = __fdiv_rn((float)y, 255.0f);
-}
-
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
   return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
 }
@@ -40,37 +34,63 @@ __device__ __forceinline__ float4 f4_scale(float k, float4 a) {
 __device__ __forceinline__ float f4_add(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float f4_scale(float k, float a) { return __fmul_rn(k, a); }
 
-// One separable pass, BORDER_REPLICATE: out = k[R]*c + sum_i k[R+i]*(p[-i] + p[+i])   (oracle blur_sep)
-template <typename T, int R, bool VERT>
-__global__ void blur_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, Taps taps) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x;
-  int y = blockIdx.y;
-  if (x >= W) return;
-  const size_t row = (size_t)y * W;
-  T acc = f4_scale(taps.k[R], in[row + x]);
+// symmetric taps in the oracle's order: k[R]*c + sum_i k[R+i]*(p[-i] + p[+i])   (oracle blur_sep)
+template <typename T, int R, typename F>
+__device__ __forceinline__ T sym_taps(const Taps& taps, F at) {
+  T acc = f4_scale(taps.k[R], at(0));
 #pragma unroll
-  for (int i = 1; i <= R; ++i) {
-    T a, b;
-    if (VERT) {
-      a = in[(size_t)max(y - i, 0) * W + x];
-      b = in[(size_t)min(y + i, H - 1) * W + x];
-    } else {
-      a = in[row + max(x - i, 0)];
-      b = in[row + min(x + i, W - 1)];
-    }
-    acc = f4_add(acc, f4_scale(taps.k[R + i], f4_add(a, b)));
-  }
-  out[row + x] = acc;
+  for (int i = 1; i <= R; ++i) acc = f4_add(acc, f4_scale(taps.k[R + i], f4_add(at(-i), at(i))));
+  return acc;
 }
 
-// central differences (Sobel ksize=1, scale 0.5, replicate) and the 4 rectified orientation layers
-__global__ void grad_layers_kernel(const float* __restrict__ g, float4* __restrict__ layers, int H, int W,
-                                   float4 kos, float4 zin) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x;
-  int y = blockIdx.y;
-  if (x >= W) return;
-  float dx = __fmul_rn(0.5f, __fsub_rn(g[(size_t)y * W + min(x + 1, W - 1)], g[(size_t)y * W + max(x - 1, 0)]));
-  float dy = __fmul_rn(0.5f, __fsub_rn(g[(size_t)min(y + 1, H - 1) * W + x], g[(size_t)max(y - 1, 0) * W + x]));
+constexpr int kTX = 32, kTY = 16;   // output tile of the fused kernels
+
+// gray (cv2 BGR2GRAY, 15-bit fixed point) / 255 -> 5x5 Gaussian (sigma 0.5) -> central differences -> the four
+// rectified orientation layers, one float4 per pixel.  All borders replicate, as cv2 does on the whole image.
+__global__ void __launch_bounds__(kTX* kTY)
+pre_layers_kernel(const uint8_t* __restrict__ bgr, float4* __restrict__ layers, int H, int W, Taps taps, float4 kos,
+                  float4 zin) {
+  constexpr int R = 2, GW = kTX + 2 * R + 2, GH = kTY + 2 * R + 2;     // gray tile with halo R + 1
+  __shared__ float g_s[GH][GW];
+  __shared__ float h_s[GH][kTX + 2];                                    // after the horizontal pass, halo 1 in x
+  __shared__ float b_s[kTY + 2][kTX + 2];                               // blurred gray, halo 1
+  const int tx = threadIdx.x % kTX, ty = threadIdx.x / kTX;
+  const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
+  for (int e = threadIdx.x; e < GW * GH; e += kTX * kTY) {
+    const int ly = e / GW, lx = e - ly * GW;
+    const int gy = min(max(y0 + ly - R - 1, 0), H - 1), gx = min(max(x0 + lx - R - 1, 0), W - 1);
+    const uint8_t* p = bgr + 3 * ((size_t)gy * W + gx);
+    const int y = (p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15;
+    g_s[ly][lx] = __fdiv_rn((float)y, 255.0f);
+  }
+  __syncthreads();
+  // horizontal pass at columns x0-1 .. x0+kTX.  The replicate border is applied to the IMAGE: column c of the
+  // padded row is the clamped image column, which is what the tile already holds.
+  for (int e = threadIdx.x; e < GH * (kTX + 2); e += kTX * kTY) {
+    const int ly = e / (kTX + 2), lx = e - ly * (kTX + 2);
+    const int gx = min(max(x0 + lx - 1, 0), W - 1);                    // image column this entry stands for
+    h_s[ly][lx] = sym_taps<float, R>(taps, [&](int i) {
+      const int c = min(max(gx + i, 0), W - 1);                        // clamped image column
+      return g_s[ly][c - (x0 - R - 1) >= 0 ? min(c - (x0 - R - 1), GW - 1) : 0];
+    });
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < (kTY + 2) * (kTX + 2); e += kTX * kTY) {
+    const int ly = e / (kTX + 2), lx = e - ly * (kTX + 2);
+    const int gy = min(max(y0 + ly - 1, 0), H - 1);
+    b_s[ly][lx] = sym_taps<float, R>(taps, [&](int i) {
+      const int r = min(max(gy + i, 0), H - 1);
+      return h_s[min(max(r - (y0 - R - 1), 0), GH - 1)][lx];
+    });
+  }
+  __syncthreads();
+  const int x = x0 + tx, y = y0 + ty;
+  if (x >= W || y >= H) return;
+  // Sobel ksize=1, scale 0.5, replicate: b_s index of image column c is c - (x0 - 1), rows alike
+  const int xl = max(x - 1, 0) - (x0 - 1), xr = min(x + 1, W - 1) - (x0 - 1);
+  const int yu = max(y - 1, 0) - (y0 - 1), yd = min(y + 1, H - 1) - (y0 - 1);
+  const float dx = __fmul_rn(0.5f, __fsub_rn(b_s[ty + 1][xr], b_s[ty + 1][xl]));
+  const float dy = __fmul_rn(0.5f, __fsub_rn(b_s[yd][tx + 1], b_s[yu][tx + 1]));
   float4 o;
   o.x = fmaxf(__fadd_rn(__fmul_rn(kos.x, dx), __fmul_rn(zin.x, dy)), 0.f);
   o.y = fmaxf(__fadd_rn(__fmul_rn(kos.y, dx), __fmul_rn(zin.y, dy)), 0.f);
@@ -79,50 +99,107 @@ __global__ void grad_layers_kernel(const float* __restrict__ g, float4* __restri
   layers[(size_t)y * W + x] = o;
 }
 
-// bilinear petal sampling (bi_get_histogram semantics): thread = (pixel, region)
-__global__ void sample_kernel(const float4* __restrict__ cubes, size_t cube_stride, float4* __restrict__ desc, int H,
-                              int W, GridPts gp) {
-  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)H * W * 17;
-  if (t >= total) return;
-  const int reg = (int)(t % 17);
-  const int pix = (int)(t / 17);
-  const int py = pix / W, px = pix - py * W;
-  const double y = (double)py + gp.dy[reg], x = (double)px + gp.dx[reg];
-  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool inside = (reg == 0) || (x >= 0.0 && x < (double)(W - 1) && y >= 0.0 && y < (double)(H - 1));
-  const int mnx = (int)x, mny = (int)y;
-  if (inside && mnx < W - 2 && mny < H - 2) {
-    const double alpha = (double)(mnx + 1) - x, beta = (double)(mny + 1) - y;
-    const float w0 = (float)(alpha * beta);
-    const float w1 = (float)(beta - (double)w0);
-    const float w2 = (float)(alpha - (double)w0);
-    const float w3 = (float)(1.0 + (double)w0 - alpha - beta);
-    const float4* c = cubes + (size_t)gp.cube[reg] * cube_stride;
-    const float4 A = c[(size_t)mny * W + mnx], C = c[(size_t)mny * W + mnx + 1];
-    const float4 B = c[(size_t)(mny + 1) * W + mnx], D = c[(size_t)(mny + 1) * W + mnx + 1];
-    o = f4_add(f4_add(f4_add(f4_scale(w0, A), f4_scale(w1, C)), f4_scale(w2, B)), f4_scale(w3, D));
+// separable Gaussian on the float4 layers, horizontal then vertical pass in one kernel through shared memory
+template <int R>
+__global__ void __launch_bounds__(kTX* kTY)
+blur_layers_kernel(const float4* __restrict__ in, float4* __restrict__ out, int H, int W, Taps taps) {
+  __shared__ float4 h_s[kTY + 2 * R][kTX];       // horizontal pass results for the rows the vertical pass needs
+  const int tx = threadIdx.x % kTX, ty = threadIdx.x / kTX;
+  const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
+  const int x = min(x0 + tx, W - 1);
+  for (int ly = ty; ly < kTY + 2 * R; ly += kTY) {
+    const int gy = min(max(y0 + ly - R, 0), H - 1);
+    const float4* rowp = in + (size_t)gy * W;
+    h_s[ly][tx] = sym_taps<float4, R>(taps, [&](int i) { return rowp[min(max(x + i, 0), W - 1)]; });
   }
-  desc[t] = o;
+  __syncthreads();
+  const int y = y0 + ty;
+  if (x0 + tx >= W || y >= H) return;
+  out[(size_t)y * W + x] = sym_taps<float4, R>(taps, [&](int i) {
+    const int r = min(max(y + i, 0), H - 1);      // clamped image row; rows y0-R .. y0+kTY-1+R are in the tile
+    return h_s[r - (y0 - R) < 0 ? 0 : r - (y0 - R)][tx];
+  });
 }
 
-template <typename T>
-static int blur2d(const T* in, T* tmp, T* out, int H, int W, int which, cudaStream_t s) {
-  const int ksize = kDaisyBlurSize[which];
+// bilinear petal sampling (bi_get_histogram semantics).  One block per 32 x 8 pixel tile: the four cubes are staged
+// in shared memory with a halo of 6, every thread produces (pixel, region) float4s such that consecutive threads
+// write consecutive 16-byte pieces of the descriptor array (the 272 B/pixel write is the HBM-bound part).
+constexpr int kSX = 32, kSY = 8, kSHalo = 6;
+constexpr int kSW = kSX + 2 * kSHalo + 1, kSH = kSY + 2 * kSHalo + 1;
+
+__global__ void __launch_bounds__(256)
+sample_kernel(const float4* __restrict__ cubes, size_t cube_stride, float4* __restrict__ desc, int H, int W, GridPts gp) {
+  extern __shared__ float4 cube_s[];             // [4][kSH][kSW]
+  __shared__ double ax_s[kSX][17], ay_s[kSY][17];
+  __shared__ int mx_s[kSX][17], my_s[kSY][17];
+  __shared__ int gcube_s[17];
+  if (threadIdx.x < 17) gcube_s[threadIdx.x] = gp.cube[threadIdx.x];
+  const int x0 = blockIdx.x * kSX, y0 = blockIdx.y * kSY;
+  for (int e = threadIdx.x; e < 4 * kSH * kSW; e += 256) {
+    const int c = e / (kSH * kSW), r = e - c * (kSH * kSW);
+    const int ly = r / kSW, lx = r - ly * kSW;
+    const int gy = y0 + ly - kSHalo, gx = x0 + lx - kSHalo;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = cubes[(size_t)c * cube_stride + (size_t)gy * W + gx];
+    cube_s[e] = v;
+  }
+  __syncthreads();
+  // per-tile tables: the double-precision coordinate arithmetic of bi_get_histogram depends on (column, region)
+  // and (row, region) separately, so it is done once per tile instead of once per (pixel, region)
+  for (int e = threadIdx.x; e < (kSX + kSY) * 17; e += 256) {
+    const int k = e / 17, reg = e - k * 17;
+    if (k < kSX) {
+      const double x = (double)(x0 + k) + gp.dx[reg];
+      const int mnx = (int)x;
+      ax_s[k][reg] = (double)(mnx + 1) - x;
+      mx_s[k][reg] = ((reg == 0) || (x >= 0.0 && x < (double)(W - 1))) && mnx < W - 2 ? mnx - x0 + kSHalo : -1;
+    } else {
+      const double y = (double)(y0 + k - kSX) + gp.dy[reg];
+      const int mny = (int)y;
+      ay_s[k - kSX][reg] = (double)(mny + 1) - y;
+      my_s[k - kSX][reg] = ((reg == 0) || (y >= 0.0 && y < (double)(H - 1))) && mny < H - 2 ? mny - y0 + kSHalo : -1;
+    }
+  }
+  __syncthreads();
+  const int ny = min(kSY, H - y0), nx = min(kSX, W - x0);
+  const int items = ny * nx * 17;                 // (pixel, region) pairs of the tile, row-major like the output
+  for (int e = threadIdx.x; e < items; e += 256) {
+    const int pixel = e / 17, reg = e - pixel * 17;
+    const int ly = pixel / nx, lx = pixel - ly * nx;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int cx = mx_s[lx][reg], cy = my_s[ly][reg];
+    if (cx >= 0 && cy >= 0) {
+      const double alpha = ax_s[lx][reg], beta = ay_s[ly][reg];
+      const float w0 = (float)(alpha * beta);
+      const double w0d = (double)w0;
+      const float w1 = (float)(beta - w0d);
+      const float w2 = (float)(alpha - w0d);
+      const float w3 = (float)(1.0 + w0d - alpha - beta);
+      const float4* c = cube_s + ((size_t)gcube_s[reg] * kSH + cy) * kSW + cx;
+      const float4 A = c[0], C = c[1], B = c[kSW], D = c[kSW + 1];
+      o = f4_add(f4_add(f4_add(f4_scale(w0, A), f4_scale(w1, C)), f4_scale(w2, B)), f4_scale(w3, D));
+    }
+    desc[((size_t)(y0 + ly) * W + x0 + lx) * 17 + reg] = o;
+  }
+}
+
+static Taps taps_of(int which) {
   Taps t{};
-  for (int i = 0; i < ksize; ++i) t.k[i] = kDaisyBlurTaps[which][i];
-  dim3 block(128), grid((W + 127) / 128, H);
-  switch (ksize / 2) {
-#define FB_BLUR_CASE(R)                                                  \
-  case R:                                                                \
-    blur_kernel<T, R, false><<<grid, block, 0, s>>>(in, tmp, H, W, t);   \
-    blur_kernel<T, R, true><<<grid, block, 0, s>>>(tmp, out, H, W, t);   \
-    break;
-    FB_BLUR_CASE(1) FB_BLUR_CASE(2) FB_BLUR_CASE(3) FB_BLUR_CASE(4)
-#undef FB_BLUR_CASE
+  for (int i = 0; i < kDaisyBlurSize[which]; ++i) t.k[i] = kDaisyBlurTaps[which][i];
+  return t;
+}
+
+static int blur_layers(const float4* in, float4* out, int H, int W, int which, cudaStream_t s) {
+  const Taps t = taps_of(which);
+  dim3 grid((W + kTX - 1) / kTX, (H + kTY - 1) / kTY);
+  switch (kDaisyBlurSize[which] / 2) {
+    case 1: blur_layers_kernel<1><<<grid, kTX * kTY, 0, s>>>(in, out, H, W, t); break;
+    case 2: blur_layers_kernel<2><<<grid, kTX * kTY, 0, s>>>(in, out, H, W, t); break;
+    case 3: blur_layers_kernel<3><<<grid, kTX * kTY, 0, s>>>(in, out, H, W, t); break;
+    case 4: blur_layers_kernel<4><<<grid, kTX * kTY, 0, s>>>(in, out, H, W, t); break;
     default: return FLOWB200_EINVAL;
   }
-  FB_LAUNCH_CHECK_N(2);
+  FB_LAUNCH_CHECK();
   return FLOWB200_OK;
 }
 
@@ -133,7 +210,7 @@ using namespace flowb200;
 extern "C" size_t flowb200_daisy_workspace_bytes(int H, int W) {
   if (H <= 0 || W <= 0) return 0;
   size_t n = (size_t)H * W;
-  return 3 * align_up(n * sizeof(float)) + 6 * align_up(n * sizeof(float4));
+  return 6 * align_up(n * sizeof(float4));
 }
 
 extern "C" int flowb200_daisy(const uint8_t* bgr, int H, int W, float* desc, void* workspace, size_t workspace_bytes,
@@ -142,30 +219,24 @@ extern "C" int flowb200_daisy(const uint8_t* bgr, int H, int W, float* desc, voi
   if (workspace_bytes < flowb200_daisy_workspace_bytes(H, W)) return FLOWB200_EWORKSPACE;
   const size_t n = (size_t)H * W;
   char* w = static_cast<char*>(workspace);
-  float* g0 = reinterpret_cast<float*>(w); w += align_up(n * sizeof(float));
-  float* g1 = reinterpret_cast<float*>(w); w += align_up(n * sizeof(float));
-  float* g2 = reinterpret_cast<float*>(w); w += align_up(n * sizeof(float));
   float4* lay = reinterpret_cast<float4*>(w); w += align_up(n * sizeof(float4));
   float4* tmp = reinterpret_cast<float4*>(w); w += align_up(n * sizeof(float4));
   float4* cubes = reinterpret_cast<float4*>(w);
   const size_t cube_stride = align_up(n * sizeof(float4)) / sizeof(float4);
 
-  gray_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(bgr, g0, (int)n);
-  FB_LAUNCH_CHECK();
-  int rc = blur2d<float>(g0, g1, g2, H, W, 0, stream);            // layered_gradient(): GaussianBlur 5x5, 0.5
-  if (rc) return rc;
+  // layered_gradient(): gray, GaussianBlur 5x5 sigma 0.5, central differences, rectified layers
   const float4 kos = make_float4(kDaisyCos[0], kDaisyCos[1], kDaisyCos[2], kDaisyCos[3]);
   const float4 zin = make_float4(kDaisySin[0], kDaisySin[1], kDaisySin[2], kDaisySin[3]);
-  dim3 block(128), grid((W + 127) / 128, H);
-  grad_layers_kernel<<<grid, block, 0, stream>>>(g2, lay, H, W, kos, zin);
+  dim3 grid((W + kTX - 1) / kTX, (H + kTY - 1) / kTY);
+  pre_layers_kernel<<<grid, kTX * kTY, 0, stream>>>(bgr, lay, H, W, taps_of(0), kos, zin);
   FB_LAUNCH_CHECK();
   // base smoothing sqrt(1.6^2 - 0.5^2), then the incremental blurs to cumulative sigma 0.625*(r+1)
-  rc = blur2d<float4>(lay, tmp, lay, H, W, 1, stream);
+  int rc = blur_layers(lay, tmp, H, W, 1, stream);
   if (rc) return rc;
-  const float4* src = lay;
+  const float4* src = tmp;
   for (int r = 0; r < 4; ++r) {
     float4* dst = cubes + (size_t)r * cube_stride;
-    rc = blur2d<float4>(src, tmp, dst, H, W, 2 + r, stream);
+    rc = blur_layers(src, dst, H, W, 2 + r, stream);
     if (rc) return rc;
     src = dst;
   }
@@ -175,9 +246,10 @@ extern "C" int flowb200_daisy(const uint8_t* bgr, int H, int W, float* desc, voi
     gp.dx[i] = kDaisyGridDx[i];
     gp.cube[i] = kDaisyGridCube[i];
   }
-  const size_t total = n * 17;
-  sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(cubes, cube_stride, reinterpret_cast<float4*>(desc),
-                                                                   H, W, gp);
+  const size_t smem = (size_t)4 * kSH * kSW * sizeof(float4);
+  FB_CUDA_CHECK(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 sgrid((W + kSX - 1) / kSX, (H + kSY - 1) / kSY);
+  sample_kernel<<<sgrid, 256, smem, stream>>>(cubes, cube_stride, reinterpret_cast<float4*>(desc), H, W, gp);
   FB_LAUNCH_CHECK();
   return FLOWB200_OK;
 }
