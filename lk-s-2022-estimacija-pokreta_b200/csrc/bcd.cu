@@ -367,10 +367,12 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
           if constexpr (sizeof(DP) == 4) {
             // int32 mode: (dp << 32 | label) keys make "lowest label wins ties" a plain 64-bit minimum; four
             // independent accumulators keep four candidates in flight
-            int t = t0;
-            for (; t + 3 < t1; t += 4) {
-              const int32_t ua = vp[t], ub = vp[t + 1], uc = vp[t + 2], ud = vp[t + 3];
-              const unsigned long long ra = rp[t], rb = rp[t + 1], rc = rp[t + 2], rd = rp[t + 3];
+            for (int t = t0; t < t1; t += 4) {
+              // groups of four; indices past the end are clamped (re-evaluating a candidate is harmless for a min)
+              const int tl = t1 - 1;
+              const int ib = min(t + 1, tl), ic = min(t + 2, tl), id = min(t + 3, tl);
+              const int32_t ua = vp[t], ub = vp[ib], uc = vp[ic], ud = vp[id];
+              const unsigned long long ra = rp[t], rb = rp[ib], rc = rp[ic], rd = rp[id];
               const int la = l1_vec(dy, dx, ua), lb = l1_vec(dy, dx, ub), lc = l1_vec(dy, dx, uc),
                         ld = l1_vec(dy, dx, ud);
               const unsigned long long ka = ra + ((unsigned long long)(uint32_t)(la << shift) << 32);
@@ -381,11 +383,6 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
               if (lb < tpsi && kb < key_b) key_b = kb;
               if (lc < tpsi && kc < key_c) key_c = kc;
               if (ld < tpsi && kd < key_d) key_d = kd;
-            }
-            for (; t < t1; ++t) {
-              const int la = l1_vec(dy, dx, vp[t]);
-              const unsigned long long ka = rp[t] + ((unsigned long long)(uint32_t)(la << shift) << 32);
-              if (la < tpsi && ka < key_a) key_a = ka;
             }
           } else {
             for (int t = t0; t < t1; ++t) {
