@@ -173,12 +173,14 @@ def cpu_oracle_pipeline(img1, img2, op, sweeps, directions, con_tresh, seed=0):
 
 
 def cpu_sample(p, sweeps, directions, steps=1):
-    """Bounded sample of the workload for the CPU oracle: a crop of 5x3 cells (every pixel of the middle
-    column of cells sees the full 5-cell search width), same K / sweeps / directions."""
+    """Bounded sample of the workload for the CPU oracle: a crop of 5x5 cells (the centre cell's pixels see the
+    full 5x5-cell search window), same K / sweeps / directions, all host threads (torchrun sets
+    OMP_NUM_THREADS=1, so the thread count is set explicitly)."""
     from oracle import cport
     from oracle.proposals import Params
     synth = mod("synth")
-    Hs, Ws = min(p.H, 3 * p.cellh), min(p.W, 5 * p.cellw)
+    cport.set_num_threads(os.cpu_count() or 1)
+    Hs, Ws = min(p.H, 5 * p.cellh), min(p.W, 5 * p.cellw)
     op = Params(Hs, Ws, p.cellw, p.cellh, p.cell_radius, p.k_cell, p.n_gauss, p.sigma, p.maxnprop, p.tphi, p.tpsi,
                 p.lamda)
     img1, img2, _, _ = synth.make_pair(Hs, Ws, 0)
@@ -192,7 +194,7 @@ def cpu_sample(p, sweeps, directions, steps=1):
         ts.append(time.perf_counter() - t0)
     t = float(np.mean(ts))
     return {"value": Hs * Ws / 1e6 / t, "unit": "Mpix/s", "cores": cport.num_threads(), "kind": "port",
-            "sample": f"{Ws}x{Hs} crop (5x3 cells of {p.cellw}x{p.cellh}), K={p.maxnprop}, bcd_times={sweeps}, "
+            "sample": f"{steps} x {Ws}x{Hs} crop (5x5 cells of {p.cellw}x{p.cellh}), K={p.maxnprop}, bcd_times={sweeps}, "
                       f"{directions} direction(s), {t:.2f} s/step; C oracle with OpenMP + numpy DAISY",
             "seconds_per_step": t}
 
@@ -331,7 +333,7 @@ def main():
                         for k, v in stages.items()}}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            r = cpu_sample(p, sweeps, directions)
+            r = cpu_sample(p, sweeps, directions, steps=2)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line = {"metric": METRIC, "value": mpix, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": W_,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -2,7 +2,7 @@
 // Reference: `python bcd.py` bcd() :101-257 (one chain), ceoBCD() :261-284 (phase order),
 // sidepsi :84-88, purepsi :98-99.  See oracle/bcd.py for the recurrence in words.
 //
-// Mapping: one CTA of 128 threads per chain, a few labels of the current pixel per thread.  All chains of a phase are
+// Mapping: one CTA per chain, one thread per label of the current pixel.  All chains of a phase are
 // independent (they read and write only their own pixels), so a phase is one launch; the four phases
 // and the sweeps are stream-ordered.  K-sets (the reference's packedksets cache, daisy i flann.py:256-309)
 // are never materialised: labels are processed in the order of a spatial hash of their flow vectors and
@@ -252,9 +252,12 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
   uint16_t* bp_chain = bp + (size_t)blockIdx.x * g.len * Kpad;
   const DP INF = DpOps<DP>::inf();
 
-  // software prefetch of the next two pixels' label data (in sorted order)
-  int n_a = 0, n_b = 0;
-  uint32_t o_a[PER], o_b[PER];
+  // software prefetch, three stages deep so that no load waits for another one's result inside a step:
+  //   stage c (pixel i+3): nprop and the order entries (independent loads)
+  //   stage b (pixel i+2): vectors and costs, addressed through the order entries fetched one step earlier
+  //   stage a (pixel i+1): complete; published to shared memory during step i
+  int n_a = 0, n_b = 0, n_c = 0;
+  uint32_t o_a[PER], o_b[PER], o_c[PER];
   int32_t v_a[PER], v_b[PER];
   CostT c_a[PER], c_b[PER];
   const ptrdiff_t pstep = (ptrdiff_t)g.ystep * W + g.xstep;        // pixel index increment per chain step
@@ -262,29 +265,38 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
   const uint32_t* f_or = order + (size_t)pixel(0) * K + l;
   const int32_t* f_pv = pvec + (size_t)pixel(0) * K;
   const CostT* f_co = cost + (size_t)pixel(0) * K;
-  auto fetch = [&](int i, int& n, uint32_t (&o)[PER], int32_t (&v)[PER], CostT (&c)[PER]) {   // i = 0, 1, 2, ...
+  auto fetch_order = [&](int i, int& n, uint32_t (&o)[PER]) {      // i = 0, 1, 2, ... in order
     n = 0;
 #pragma unroll
-    for (int r = 0; r < PER; ++r) { o[r] = 0; v[r] = 0; c[r] = CostT(0); }
+    for (int r = 0; r < PER; ++r) o[r] = 0;
     if (i < g.len) {
       n = *f_np;
 #pragma unroll
       for (int r = 0; r < PER; ++r)
-        if (l + r * T < n) o[r] = f_or[r * T];
+        if (l + r * T < K) o[r] = f_or[r * T];                     // entries >= nprop are unused (masked below)
+      f_np += pstep;
+      f_or += pstep * K;
+    }
+  };
+  auto fetch_data = [&](int i, int n, const uint32_t (&o)[PER], int32_t (&v)[PER], CostT (&c)[PER]) {
+#pragma unroll
+    for (int r = 0; r < PER; ++r) { v[r] = 0; c[r] = CostT(0); }
+    if (i < g.len) {
 #pragma unroll
       for (int r = 0; r < PER; ++r)
         if (l + r * T < n) {
           v[r] = f_pv[o[r] & 1023];
           c[r] = f_co[o[r] & 1023];
         }
-      f_np += pstep;
-      f_or += pstep * K;
       f_pv += pstep * K;
       f_co += pstep * K;
     }
   };
-  fetch(0, n_a, o_a, v_a, c_a);
-  fetch(1, n_b, o_b, v_b, c_b);
+  fetch_order(0, n_a, o_a);
+  fetch_order(1, n_b, o_b);
+  fetch_order(2, n_c, o_c);
+  fetch_data(0, n_a, o_a, v_a, c_a);
+  fetch_data(1, n_b, o_b, v_b, c_b);
   DP dpv[PER];
   int orig[PER];
   int key0[PER], key1[PER], key2[PER];   // buckets opened 0 / 1 / 2 builds ago (emptied after their query)
@@ -326,9 +338,12 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
     for (int r = 0; r < PER; ++r) {
       of[r] = o_a[r]; v[r] = v_a[r]; c[r] = c_a[r];
       o_a[r] = o_b[r]; v_a[r] = v_b[r]; c_a[r] = c_b[r];
+      o_b[r] = o_c[r];
     }
     n_a = n_b;
-    fetch(i + 2, n_b, o_b, v_b, c_b);
+    n_b = n_c;
+    fetch_data(i + 2, n_b, o_b, v_b, c_b);       // addresses come from order entries loaded a step ago
+    fetch_order(i + 3, n_c, o_c);
     const int cur = i & 1, prv = cur ^ 1;
     uint32_t* rng_q = rng_s + ((i + 2) % 3) * kHashSize;   // ranges of pixel i-1, queried now
     uint32_t* rng_c = rng_s + ((i + 1) % 3) * kHashSize;   // ranges of pixel i-2 (queried at step i-1): emptied now,
@@ -552,13 +567,15 @@ static int launch_sweeps(const int32_t* pvec, const CostT* cost, const int32_t* 
                          int K, double lamda, int tpsi, int shift, int sweeps, int32_t* labels_per_sweep, uint16_t* bp,
                          uint32_t* order, cudaStream_t stream) {
   const int Kpad = (K + 31) / 32 * 32;
-  constexpr int T = 128;
+  // one label per thread: the thread count is Kpad rounded up to the next instantiated size
   void (*kern)(const int32_t*, const CostT*, const int32_t*, const uint32_t*, int32_t*, uint16_t*, int, int, int, int,
-               int, double, int, int, int);
-  if (K <= T) kern = bcd_chain_kernel<DP, CostT, T, 1, 4>;
-  else if (K <= 2 * T) kern = bcd_chain_kernel<DP, CostT, T, 2, 4>;
-  else if (K <= 3 * T) kern = bcd_chain_kernel<DP, CostT, T, 3, 4>;
-  else kern = bcd_chain_kernel<DP, CostT, T, 4, 3>;
+               int, double, int, int, int) = nullptr;
+  int T = 0;
+#define FB_BCD_CASE(TT, MB) if (!kern && K <= TT) { kern = bcd_chain_kernel<DP, CostT, TT, 1, MB>; T = TT; }
+  FB_BCD_CASE(64, 8) FB_BCD_CASE(128, 6) FB_BCD_CASE(192, 5) FB_BCD_CASE(256, 4) FB_BCD_CASE(320, 4)
+  FB_BCD_CASE(384, 3) FB_BCD_CASE(512, 2)
+#undef FB_BCD_CASE
+  if (!kern) return FLOWB200_EUNSUPPORTED;
   const int maxlen = H > W ? H : W;
   size_t smem = (size_t)Kpad * (2 * sizeof(typename RepT<DP>::type) + 2 * sizeof(DP) + 16) + 32 * (sizeof(DP) + 4) +
                 3 * (size_t)kHashSize * 4 + (size_t)maxlen * 4;
