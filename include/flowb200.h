@@ -97,8 +97,9 @@ int flowb200_knn_proposals(const float* desc_src, const float* desc_tgt, const f
 
 /* diagnostics of the FLOWB200_KNN_TCGEN05 path: geom_out_host (host int32[8]) = {Tpad, stride s of the target
  * permutation pos -> idx = pos*s mod T, tiles_x, tiles_y, n_items, tile_w, tile_h, max candidates};
- * scores (optional, device float32 [n_items][128][Tpad]) = raw tensor-core ranking scores of every
- * (cell, 16x8 query tile) work item, item = cell*tiles_x*tiles_y + tile.  Synchronises. */
+ * scores (optional, device float32 [n_items][tile_w*tile_h][Tpad]) = raw tensor-core ranking scores of every
+ * (tile_w x tile_h query pixels, cell) work item, item = tile*n_cells + cell; the rows of an item are tile_w/16
+ * consecutive 16 x tile_h MMA tiles of 128 rows.  Synchronises. */
 int flowb200_knn_debug_scores(const float* desc_src, const float* desc_tgt, const flowb200_params* p, float* scores,
                               int32_t* geom_out_host, void* workspace, size_t workspace_bytes,
                               flowb200_stream_t stream);

@@ -21,12 +21,15 @@
 //                     the CPU oracle), rank by (distance, index), write the k proposals + float32 L1 data costs.
 //     knn_fallback_kernel  (query, cell) pairs whose lists overflowed are redone by brute force.
 //
-// One CTA = one 16x8-pixel query tile x one target cell at a time (persistent over a static work list), 6 warps:
-// warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue (one TMEM lane quadrant each).
-// Two CTAs are resident per SM (256 TMEM columns each) so one CTA's selection overlaps the other's MMAs.
+// One CTA = two x-adjacent 16x8-pixel query tiles x one target cell at a time (persistent over a static work
+// list), 10 warps: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 / 6-9 the epilogues of tile
+// 0 / 1 (one TMEM lane quadrant each).  Every 20 KB target chunk is multiplied with both tiles: the kernel is
+// bound by the L2 -> shared-memory stream of the target operand (measured: ~3.3 TB/s with nothing else running),
+// so the bytes per query matter more than anything else.  One CTA per SM owns all 512 TMEM columns.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -36,16 +39,17 @@ namespace flowb200 {
 constexpr int kKP = 80;            // padded contraction depth (5 x k16)
 constexpr int kKB = 5;             // k16 blocks
 constexpr float kScale = 64.0f;    // descriptors are < ~0.5: keeps fp16 values far from subnormals
-constexpr int kTileW = 16, kTileH = 8, kTileM = 128;
+constexpr int kTileW = 16, kTileH = 8, kTileM = 128;   // one MMA tile: 16 x 8 query pixels
+constexpr int kTilesPerItem = 2;                        // a work item is two x-adjacent tiles (32 x 8 pixels)
 constexpr int kChunkN = 128;       // targets per accumulator stage
-constexpr int kBStages = 2;
+constexpr int kBStages = 3;
 constexpr int kAccStages = 2;
-constexpr int kTmemCols = kAccStages * kChunkN;          // 256
+constexpr int kTmemCols = kAccStages * kTilesPerItem * kChunkN;   // 512: the whole TMEM, one CTA per SM
 constexpr int kSlabBytes = kTileM * 32;                  // one k16 block of 128 rows: 4096 B
 constexpr int kTileBytes = kKB * kSlabBytes;             // 20480 B
 constexpr int kListCap = 96;       // per-row candidate list in shared memory (compacted when > kListCap - 8)
 constexpr int kCand = 32;          // candidates handed to the exact re-rank per (query, cell)
-constexpr int kSelThreads = 192;
+constexpr int kSelThreads = 64 + 128 * kTilesPerItem;     // TMA warp, MMA warp, 4 epilogue warps per tile
 constexpr float kPadNorm = 60000.0f;   // n_hi of padding target rows: their score can never be selected
 
 struct KnnTcGeom {
@@ -100,6 +104,17 @@ __global__ void knn_prep_query_kernel(const float* __restrict__ desc, int npix, 
   }
 }
 
+// Target operand layout: [cell][chunk of kChunkN targets][k16 block][row][16 halves], every (chunk, k16 block) slab
+// already in the 32-byte-swizzled form the UMMA descriptor expects (byte-offset bit 4 ^= bit 7, i.e. the two
+// 16-byte halves of rows 4-7 of every 8-row group are exchanged).  One chunk is then ONE contiguous 20 KB bulk
+// copy instead of 5 x 128 strided 32-byte rows, which is what the L2 -> shared-memory path needs to run fast.
+__device__ __forceinline__ size_t tgt_off(int cell, int nchunks, int pos, int j) {
+  const int chunk = pos / kChunkN, row = pos - chunk * kChunkN;
+  const int kb = j >> 4, jj = j & 15;
+  const int h16 = (jj >> 3) ^ ((row >> 2) & 1);
+  return (((size_t)cell * nchunks + chunk) * kKB + kb) * (size_t)(kChunkN * 16) + row * 16 + h16 * 8 + (jj & 7);
+}
+
 // one warp per (cell, pos).  cellinfo[cell] = (max rt, max Nt, max n) as float bit patterns (atomicMax on ints)
 __global__ void knn_prep_target_kernel(const float* __restrict__ desc, KnnTcGeom g, __half* __restrict__ out,
                                        int* __restrict__ cellinfo) {
@@ -108,9 +123,9 @@ __global__ void knn_prep_target_kernel(const float* __restrict__ desc, KnnTcGeom
   const int ncell = g.ncellx * g.ncelly;
   if (w >= ncell * g.Tpad) return;
   const int cell = w / g.Tpad, pos = w - cell * g.Tpad;
-  __half* o = out + (size_t)w * kKP;
+  const int nchunks = g.Tpad / kChunkN;
   if (pos >= g.T) {   // padding row
-    for (int j = lane; j < kKP; j += 32) o[j] = __float2half_rn(j == kDescDim ? kPadNorm : 0.f);
+    for (int j = lane; j < kKP; j += 32) out[tgt_off(cell, nchunks, pos, j)] = __float2half_rn(j == kDescDim ? kPadNorm : 0.f);
     return;
   }
   const int idx = (int)(((long long)pos * g.stride_s) % g.T);
@@ -126,7 +141,7 @@ __global__ void knn_prep_target_kernel(const float* __restrict__ desc, KnnTcGeom
     r2 = fmaf(e, e, r2);
     n2 = fmaf(hv, hv, n2);
     s2 = fmaf(v, v, s2);
-    o[j] = __float2half_rn(-hv);
+    out[tgt_off(cell, nchunks, pos, j)] = __float2half_rn(-hv);
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
@@ -142,8 +157,8 @@ __global__ void knn_prep_target_kernel(const float* __restrict__ desc, KnnTcGeom
   const float r1 = r0 - __half2float(h1);
   const __half h2 = __float2half_rn(r1);
   for (int j = kDescDim + lane; j < kKP; j += 32) {
-    o[j] = j == kDescDim ? h0 : j == kDescDim + 1 ? h1 : j == kDescDim + 2 ? h2
-           : j < kDescDim + 6 ? __float2half_rn(1.0f) : __float2half_rn(0.f);
+    out[tgt_off(cell, nchunks, pos, j)] = j == kDescDim ? h0 : j == kDescDim + 1 ? h1 : j == kDescDim + 2 ? h2
+                                          : j < kDescDim + 6 ? __float2half_rn(1.0f) : __float2half_rn(0.f);
   }
   if (lane == 0) {
     // n as computed here differs from the exact |t~|^2/2 by fp32 rounding of n2: folded into rt's slack
@@ -193,38 +208,39 @@ __device__ __noinline__ int list_compact(uint32_t* lst, int cnt, float bound) {
 // decode a work item; returns false when the tile lies outside the cell's query band
 __device__ __forceinline__ bool decode_item(const KnnTcGeom& g, int item, int& cell, int& qx0, int& qy0, int& x1,
                                             int& y1) {
-  const int tiles = g.tiles_x * g.tiles_y;
-  cell = item / tiles;
-  const int t = item - cell * tiles;
+  // cell-minor order: CTAs running at the same time stream DIFFERENT cells' targets, which spreads the L2 load
+  // over all slices (with cell-major order every SM hammered the same 300 KB and the L2 slices holding it)
+  const int ncell = g.ncellx * g.ncelly;
+  const int t = item / ncell;
+  cell = item - t * ncell;
   const int tyi = t / g.tiles_x, txi = t - tyi * g.tiles_x;
   const int ci = cell % g.ncellx, cj = cell / g.ncellx;
   const int x0 = max(0, g.cellw * (ci - g.R)), y0 = max(0, g.cellh * (cj - g.R));
   x1 = min(g.W, g.cellw * (ci + g.R + 1));
   y1 = min(g.H, g.cellh * (cj + g.R + 1));
-  qx0 = x0 + txi * kTileW;
+  qx0 = x0 + txi * kTileW * kTilesPerItem;
   qy0 = y0 + tyi * kTileH;
   return qx0 < x1 && qy0 < y1;
 }
 
 template <int KC, bool DBG>
-__global__ void __launch_bounds__(kSelThreads, 2)
-knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_t, KnnTcGeom g,
+__global__ void __launch_bounds__(kSelThreads, 1)
+knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __restrict__ t16, KnnTcGeom g,
                   int n_items, const float2* __restrict__ qinfo, const int* __restrict__ cellinfo,
                   uint16_t* __restrict__ cand, uint8_t* __restrict__ cand_cnt, int32_t* __restrict__ counters,
-                  int counters_on, float* __restrict__ dbg_scores) {
+                  int counters_on, int experiment, float* __restrict__ dbg_scores) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + kTileBytes;
-  uint32_t* list_e = reinterpret_cast<uint32_t*>(smem + kTileBytes * (1 + kBStages));      // [kListCap][128]
-  SelSmem* ss = reinterpret_cast<SelSmem*>(list_e + kListCap * kTileM);
+  uint8_t* sA = smem;                                                                     // [tile][5 slabs]
+  uint8_t* sB = smem + kTileBytes * kTilesPerItem;                                         // [stage][5 slabs]
+  uint32_t* list_e = reinterpret_cast<uint32_t*>(smem + kTileBytes * (kTilesPerItem + kBStages));   // [tile][kListCap][128]
+  SelSmem* ss = reinterpret_cast<SelSmem*>(list_e + kTilesPerItem * kListCap * kTileM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = g.Tpad / kChunkN;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_q);
-    ptx::prefetch_tmap(&tmap_t);
     ptx::mbar_init(&ss->a_full, 1);
     ptx::mbar_init(&ss->a_empty, 1);
     for (int i = 0; i < kBStages; ++i) {
@@ -233,7 +249,7 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     }
     for (int i = 0; i < kAccStages; ++i) {
       ptx::mbar_init(&ss->t_full[i], 1);
-      ptx::mbar_init(&ss->t_empty[i], 4);      // one arrival per epilogue warp
+      ptx::mbar_init(&ss->t_empty[i], 4 * kTilesPerItem);      // one arrival per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -251,16 +267,25 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         int cell, qx0, qy0, x1, y1;
         if (!decode_item(g, item, cell, qx0, qy0, x1, y1)) continue;
         ptx::mbar_wait_backoff(&ss->a_empty, (it & 1) ^ 1, 2000);
-        ptx::mbar_arrive_expect_tx(&ss->a_full, kTileBytes);
+        if (experiment == 79) { ptx::mbar_arrive(&ss->a_full); } else {
+        ptx::mbar_arrive_expect_tx(&ss->a_full, kTileBytes * kTilesPerItem);
 #pragma unroll
-        for (int kb = 0; kb < kKB; ++kb) ptx::tma_load_3d(sA + kb * kSlabBytes, &tmap_q, &ss->a_full, kb * 16, qx0, qy0);
-        for (int c = 0; c < nchunks; ++c, ++bcount) {
-          const uint32_t st = bcount % kBStages, ph = (bcount / kBStages) & 1;
-          ptx::mbar_wait_backoff(&ss->b_empty[st], ph ^ 1, 2000);
-          ptx::mbar_arrive_expect_tx(&ss->b_full[st], kTileBytes);
+        for (int m = 0; m < kTilesPerItem; ++m)
 #pragma unroll
           for (int kb = 0; kb < kKB; ++kb)
-            ptx::tma_load_3d(sB + st * kTileBytes + kb * kSlabBytes, &tmap_t, &ss->b_full[st], kb * 16, c * kChunkN, cell);
+            ptx::tma_load_3d(sA + m * kTileBytes + kb * kSlabBytes, &tmap_q, &ss->a_full, kb * 16, qx0 + m * kTileW, qy0);
+        }
+        for (int c = 0; c < nchunks; ++c, ++bcount) {
+          const uint32_t st = bcount % kBStages, ph = (bcount / kBStages) & 1;
+          ptx::mbar_wait_backoff(&ss->b_empty[st], ph ^ 1, 100);
+          ptx::mbar_arrive_expect_tx(&ss->b_full[st], kTileBytes);
+          // several smaller copies per chunk: the TMA engine overlaps independent copies but moves a single one
+          // with limited memory-level parallelism
+          constexpr int kSplit = 10, kPiece = kTileBytes / kSplit;
+          const __half* src = t16 + ((size_t)cell * nchunks + c) * (kTileBytes / 2);
+#pragma unroll
+          for (int q = 0; q < kSplit; ++q)
+            ptx::bulk_load(sB + st * kTileBytes + q * kPiece, src + q * (kPiece / 2), kPiece, &ss->b_full[st]);
         }
         ++it;
       }
@@ -277,15 +302,22 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         for (int c = 0; c < nchunks; ++c, ++bcount) {
           const uint32_t st = bcount % kBStages, ph = (bcount / kBStages) & 1;
           const uint32_t acc = bcount % kAccStages, aph = (bcount / kAccStages) & 1;
-          ptx::mbar_wait_backoff(&ss->b_full[st], ph, 1000);
-          ptx::mbar_wait_backoff(&ss->t_empty[acc], aph ^ 1, 1000);
+          ptx::mbar_wait_backoff(&ss->b_full[st], ph, 100);
+          if (experiment != 80) ptx::mbar_wait_backoff(&ss->t_empty[acc], aph ^ 1, 100);
           ptx::tc_fence_after();
-#pragma unroll
-          for (int kb = 0; kb < kKB; ++kb) {
-            const uint64_t da = ptx::umma_desc_k_sw32(ptx::smem_u32(sA + kb * kSlabBytes));
-            const uint64_t db = ptx::umma_desc_k_sw32(ptx::smem_u32(sB + st * kTileBytes + kb * kSlabBytes));
-            ptx::mma_f16_ss(tmem_base + acc * kChunkN, da, db, idesc, kb > 0 ? 1u : 0u);
+          if (experiment >= 78) {   // timing experiment: TMA streaming only, no MMA
+            ptx::mbar_arrive(&ss->b_empty[st]);
+            if (experiment != 80) ptx::mbar_arrive(&ss->t_full[acc]);
+            continue;
           }
+#pragma unroll
+          for (int m = 0; m < kTilesPerItem; ++m)
+#pragma unroll
+            for (int kb = 0; kb < kKB; ++kb) {
+              const uint64_t da = ptx::umma_desc_k_sw32(ptx::smem_u32(sA + m * kTileBytes + kb * kSlabBytes));
+              const uint64_t db = ptx::umma_desc_k_sw32(ptx::smem_u32(sB + st * kTileBytes + kb * kSlabBytes));
+              ptx::mma_f16_ss(tmem_base + (acc * kTilesPerItem + m) * kChunkN, da, db, idesc, kb > 0 ? 1u : 0u);
+            }
           ptx::mma_commit(&ss->b_empty[st]);     // B stage reusable once these MMAs have read it
           ptx::mma_commit(&ss->t_full[acc]);     // accumulator stage complete
         }
@@ -296,14 +328,15 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   } else {
     // ===================== selection epilogue =====================
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
+    const int mt = (warp - 2) >> 2;              // which of the item's tiles this warp serves
     const int row = quad * 32 + lane;            // query row of the tile = TMEM lane
-    uint32_t* my_list = list_e + row;            // candidate list of this row: [entry][row]
+    uint32_t* my_list = list_e + mt * kListCap * kTileM + row;   // candidate list of this row: [entry][row]
     const uint32_t list_base = ptx::smem_u32(my_list);
     uint32_t bcount = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int cell, qx0, qy0, x1, y1;
       if (!decode_item(g, item, cell, qx0, qy0, x1, y1)) continue;
-      const int px = qx0 + (row & (kTileW - 1)), py = qy0 + (row >> 4);
+      const int px = qx0 + mt * kTileW + (row & (kTileW - 1)), py = qy0 + (row >> 4);
       const bool valid = px < x1 && py < y1;
       const int pix = valid ? py * g.W + px : 0;
       // eps >= |a - exact score| for every target of the cell (see file header)
@@ -326,7 +359,7 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         if constexpr (DBG) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            dbg_scores[((size_t)item * kTileM + row) * g.Tpad + pos0 + j] = __uint_as_float(r[j]);
+            dbg_scores[((size_t)(item * kTilesPerItem + mt) * kTileM + row) * g.Tpad + pos0 + j] = __uint_as_float(r[j]);
         }
         if (first) {   // first group of the cell: 16 pair minima (distinct elements) seed the list
 #pragma unroll
@@ -373,10 +406,17 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
       for (int c = 0; c < nchunks; ++c, ++bcount) {
         const uint32_t acc = bcount % kAccStages, aph = (bcount / kAccStages) & 1;
-        ptx::mbar_wait_backoff(&ss->t_full[acc], aph, 500);
+        if (experiment == 80) continue;
+        ptx::mbar_wait_backoff(&ss->t_full[acc], aph, 100);
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kChunkN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (acc * kTilesPerItem + mt) * kChunkN;
         const int cpos = c * kChunkN;
+        if (experiment >= 77) {   // timing experiment: TMA + MMA pipeline only
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&ss->t_empty[acc]);
+          continue;
+        }
         uint32_t r0[32], r1[32];
         ptx::tmem_ld_32x32(taddr, r0);
         ptx::tmem_ld_wait();
@@ -398,6 +438,7 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       }
       const int cnt = (int)((waddr - list_base) >> 9);
       // end of the cell: filter with the final bound, emit candidate target indices
+      int ns_stat = 0;
       if (valid) {
         const int ci = cell % g.ncellx, cj = cell / g.ncellx;
         int cimin, cimax, cjmin, cjmax;
@@ -417,7 +458,11 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         cand_cnt[task] = (overflow || ns > kCand) ? 255 : (uint8_t)ns;
         if (overflow) atomicAdd(counters + 1, 1);          // diagnostics (rare)
         else if (ns > kCand) atomicAdd(counters + 2, 1);
-        else if (counters_on) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 4), (unsigned long long)ns);
+        else ns_stat = ns;
+      }
+      if (counters_on) {   // diagnostics: one atomic per warp and cell
+        const int tot = __reduce_add_sync(0xffffffffu, ns_stat);
+        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 4), (unsigned long long)tot);
       }
     }
   }
@@ -712,7 +757,7 @@ static KnnTcGeom make_tc_geom(const flowb200_params* p) {
   while (gcd_i(s, g.T) != 1) ++s;
   g.stride_s = s;
   const int r = 2 * g.R + 1;
-  g.tiles_x = (min(g.W, r * g.cellw) + kTileW - 1) / kTileW;
+  g.tiles_x = (min(g.W, r * g.cellw) + kTileW * kTilesPerItem - 1) / (kTileW * kTilesPerItem);
   g.tiles_y = (min(g.H, r * g.cellh) + kTileH - 1) / kTileH;
   g.nblk = r * r;
   return g;
@@ -729,7 +774,7 @@ static TcLayout tc_layout(const flowb200_params* p) {
   const size_t n = (size_t)g.H * g.W, ncell = (size_t)g.ncellx * g.ncelly;
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off += align_up(b, 1024); return o; };
-  L.grid = 2 * kNumSMs;
+  L.grid = kNumSMs;
   L.fb_cap = 1 << 20;
   L.q16 = take(n * kKP * 2);
   L.t16 = take(ncell * g.Tpad * kKP * 2);
@@ -774,15 +819,15 @@ static int run_tc(const float* desc_src, const float* desc_tgt, const flowb200_p
   knn_prep_target_kernel<<<(unsigned)((tw * 32 + 255) / 256), 256, 0, stream>>>(desc_tgt, g, t16, cellinfo);
   FB_LAUNCH_CHECK();
 
-  CUtensorMap mq, mt;
+  CUtensorMap mq;
   if (!make_map(&mq, q16, (uint64_t)g.W, (uint64_t)g.H, kTileW, kTileH)) return FLOWB200_ECUDA;
-  if (!make_map(&mt, t16, (uint64_t)g.Tpad, (uint64_t)ncell, kChunkN, 1)) return FLOWB200_ECUDA;
   const int n_items = ncell * g.tiles_x * g.tiles_y;
-  const size_t smem = (size_t)kTileBytes * (1 + kBStages) + (size_t)kListCap * kTileM * 4 + sizeof(SelSmem) + 1024;
+  const size_t smem = (size_t)kTileBytes * (kTilesPerItem + kBStages) + (size_t)kTilesPerItem * kListCap * kTileM * 4 +
+                      sizeof(SelSmem) + 1024;
   auto kern = dbg_scores ? knn_select_kernel<KC, true> : knn_select_kernel<KC, false>;
   FB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(L.grid, n_items);
-  kern<<<grid, kSelThreads, smem, stream>>>(mq, mt, g, n_items, qinfo, cellinfo, cand, cnt, fb_count, stats != nullptr, dbg_scores);
+  kern<<<grid, kSelThreads, smem, stream>>>(mq, t16, g, n_items, qinfo, cellinfo, cand, cnt, fb_count, stats != nullptr, getenv("FLOWB200_KNN_EXPERIMENT") ? atoi(getenv("FLOWB200_KNN_EXPERIMENT")) : 0, dbg_scores);
   FB_LAUNCH_CHECK();
 
   const unsigned rgrid = (unsigned)((n * 16 + 255) / 256);
@@ -824,7 +869,7 @@ int knn_tc_debug_scores(const float* desc_src, const float* desc_tgt, const flow
   if (geom_out_host) {
     geom_out_host[0] = g.Tpad; geom_out_host[1] = g.stride_s; geom_out_host[2] = g.tiles_x;
     geom_out_host[3] = g.tiles_y; geom_out_host[4] = g.ncellx * g.ncelly * g.tiles_x * g.tiles_y;
-    geom_out_host[5] = kTileW; geom_out_host[6] = kTileH; geom_out_host[7] = kCand;
+    geom_out_host[5] = kTileW * kTilesPerItem; geom_out_host[6] = kTileH; geom_out_host[7] = kCand;
   }
   if (!scores) return FLOWB200_OK;
   if (workspace_bytes < L.total) return FLOWB200_EWORKSPACE;

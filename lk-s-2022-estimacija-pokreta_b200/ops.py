@@ -190,7 +190,10 @@ def pair_workspace(p: FlowParams, device, bcd_mode=_lib.BCD_FP64_F32COST):
 
 
 def knn_debug_scores(desc_src, desc_tgt, p: FlowParams):
-    """Diagnostics of the tcgen05 prefilter: (scores float32 [n_items][128][Tpad], geom dict)."""
+    """Diagnostics of the tcgen05 prefilter: (scores float32 [n_items][tile_w*tile_h][Tpad], geom dict).
+
+    item = tile * n_cells + cell (cell-minor work order); a work item is tile_w x tile_h query pixels stored as
+    tile_w/16 consecutive 16 x tile_h MMA tiles of 128 rows each (row = 16-wide x index + 16 * y)."""
     import numpy as np
     lib = _lib.load()
     cp = cparams(p, knn_mode=_lib.KNN_TCGEN05)
@@ -200,7 +203,8 @@ def knn_debug_scores(desc_src, desc_tgt, p: FlowParams):
                "flowb200_knn_debug_scores(geom)")
     names = ("Tpad", "stride_s", "tiles_x", "tiles_y", "n_items", "tile_w", "tile_h", "max_cand")
     g = {k: int(v) for k, v in zip(names, geom)}
-    scores = torch.full((g["n_items"], 128, g["Tpad"]), float("nan"), dtype=torch.float32, device=desc_src.device)
+    scores = torch.full((g["n_items"], g["tile_w"] * g["tile_h"], g["Tpad"]), float("nan"), dtype=torch.float32,
+                        device=desc_src.device)
     ws = _workspace(lib.flowb200_knn_workspace_bytes(C.byref(cp)), desc_src.device)
     _lib.check(lib.flowb200_knn_debug_scores(_ptr(desc_src, torch.float32), _ptr(desc_tgt, torch.float32), C.byref(cp),
                                              _ptr(scores), C.c_void_p(geom.ctypes.data), _ptr(ws), ws.numel(), _stream()),

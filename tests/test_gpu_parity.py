@@ -188,13 +188,14 @@ def test_tcgen05_scores_match_fp16_operands():
         y0, y1 = max(0, ch * (cj - R)), min(H, ch * (cj + R + 1))
         for tyi in range(g["tiles_y"]):
             for txi in range(g["tiles_x"]):
-                qx0, qy0 = x0 + txi * 16, y0 + tyi * 8
-                item = cell * g["tiles_x"] * g["tiles_y"] + tyi * g["tiles_x"] + txi
+                qx0, qy0 = x0 + txi * g["tile_w"], y0 + tyi * g["tile_h"]
+                item = (tyi * g["tiles_x"] + txi) * (ncx * ncy) + cell           # cell-minor work order
                 if qx0 >= x1 or qy0 >= y1:
                     assert np.isnan(scores[item]).all()          # skipped work item
                     continue
-                for row in (0, 17, 127, 64):
-                    px, py = qx0 + (row & 15), qy0 + (row >> 4)
+                for row in (0, 17, 127, 64, 128, 200, 255):
+                    mt, rr = row // 128, row % 128               # MMA tile inside the item, row inside the tile
+                    px, py = qx0 + mt * 16 + (rr & 15), qy0 + (rr >> 4)
                     if px >= W or py >= H:
                         continue                                  # zero-filled TMA rows
                     mq = np.float32(0.5 * (q16[py, px] ** 2).sum())
