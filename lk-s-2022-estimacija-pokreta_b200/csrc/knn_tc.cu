@@ -21,11 +21,12 @@
 //                     the CPU oracle), rank by (distance, index), write the k proposals + float32 L1 data costs.
 //     knn_fallback_kernel  (query, cell) pairs whose lists overflowed are redone by brute force.
 //
-// One CTA = two x-adjacent 16x8-pixel query tiles x one target cell at a time (persistent over a static work
-// list), 10 warps: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 / 6-9 the epilogues of tile
-// 0 / 1 (one TMEM lane quadrant each).  Every 20 KB target chunk is multiplied with both tiles: the kernel is
-// bound by the L2 -> shared-memory stream of the target operand (measured: ~3.3 TB/s with nothing else running),
-// so the bytes per query matter more than anything else.  One CTA per SM owns all 512 TMEM columns.
+// One CTA = one 16x8-pixel query tile x one target cell at a time (persistent over a static work list), 6 warps:
+// warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue (one TMEM lane quadrant each).
+// Two CTAs are resident per SM (256 TMEM columns each) so one CTA's selection overlaps the other's MMAs.
+// Measured with the epilogue switched off (FLOWB200_KNN_EXPERIMENT=77/78): the TMA stream alone takes 1.8 ms and
+// TMA + tcgen05.mma 2.8 ms per direction (tensor pipe 53 % busy); the selection epilogue is what bounds the
+// kernel (~14 ms), at ~10 issue slots per score and two epilogue warps per scheduler.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
@@ -40,11 +41,13 @@ constexpr int kKP = 80;            // padded contraction depth (5 x k16)
 constexpr int kKB = 5;             // k16 blocks
 constexpr float kScale = 64.0f;    // descriptors are < ~0.5: keeps fp16 values far from subnormals
 constexpr int kTileW = 16, kTileH = 8, kTileM = 128;   // one MMA tile: 16 x 8 query pixels
-constexpr int kTilesPerItem = 2;                        // a work item is two x-adjacent tiles (32 x 8 pixels)
+constexpr int kTilesPerItem = 1;                        // MMA tiles (x-adjacent) per work item; 2 halves the target
+                                                         // stream but leaves one CTA per SM (measured slower: the
+                                                         // selection epilogue, not the stream, bounds the kernel)
 constexpr int kChunkN = 128;       // targets per accumulator stage
-constexpr int kBStages = 3;
+constexpr int kBStages = 2;
 constexpr int kAccStages = 2;
-constexpr int kTmemCols = kAccStages * kTilesPerItem * kChunkN;   // 512: the whole TMEM, one CTA per SM
+constexpr int kTmemCols = kAccStages * kTilesPerItem * kChunkN;   // 256: two CTAs per SM
 constexpr int kSlabBytes = kTileM * 32;                  // one k16 block of 128 rows: 4096 B
 constexpr int kTileBytes = kKB * kSlabBytes;             // 20480 B
 constexpr int kListCap = 96;       // per-row candidate list in shared memory (compacted when > kListCap - 8)
@@ -224,7 +227,7 @@ __device__ __forceinline__ bool decode_item(const KnnTcGeom& g, int item, int& c
 }
 
 template <int KC, bool DBG>
-__global__ void __launch_bounds__(kSelThreads, 1)
+__global__ void __launch_bounds__(kSelThreads, 2 / kTilesPerItem)
 knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __restrict__ t16, KnnTcGeom g,
                   int n_items, const float2* __restrict__ qinfo, const int* __restrict__ cellinfo,
                   uint16_t* __restrict__ cand, uint8_t* __restrict__ cand_cnt, int32_t* __restrict__ counters,
@@ -281,7 +284,7 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __re
           ptx::mbar_arrive_expect_tx(&ss->b_full[st], kTileBytes);
           // several smaller copies per chunk: the TMA engine overlaps independent copies but moves a single one
           // with limited memory-level parallelism
-          constexpr int kSplit = 10, kPiece = kTileBytes / kSplit;
+          constexpr int kSplit = 1, kPiece = kTileBytes / kSplit;
           const __half* src = t16 + ((size_t)cell * nchunks + c) * (kTileBytes / 2);
 #pragma unroll
           for (int q = 0; q < kSplit; ++q)
@@ -774,7 +777,7 @@ static TcLayout tc_layout(const flowb200_params* p) {
   const size_t n = (size_t)g.H * g.W, ncell = (size_t)g.ncellx * g.ncelly;
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off += align_up(b, 1024); return o; };
-  L.grid = kNumSMs;
+  L.grid = (2 / kTilesPerItem) * kNumSMs;
   L.fb_cap = 1 << 20;
   L.q16 = take(n * kKP * 2);
   L.t16 = take(ncell * g.Tpad * kKP * 2);
