@@ -145,10 +145,8 @@ def stage_breakdown(ops, lib, p, sweeps, directions, g0, g1, bcd_mode, reps=2):
             timed("random", lambda: ops.random_proposals(src, tgt, p, pv, lc, npr, lab, seed=di))
 
             def run_bcd():
-                cost = lc
-                if bcd_mode == lib.BCD_INT32:
-                    cost = ops.quantise_costs(lc, p.lamda, p.cost_shift)
-                ops.bcd(pv, cost, npr, lab, sweeps, mode=bcd_mode, lamda=p.lamda, tpsi=p.tpsi, cost_shift=p.cost_shift)
+                mode = lib.BCD_INT32_F32COST if bcd_mode == lib.BCD_INT32 else bcd_mode   # as flowb200_flow_pair does
+                ops.bcd(pv, lc, npr, lab, sweeps, mode=mode, lamda=p.lamda, tpsi=p.tpsi, cost_shift=p.cost_shift)
             timed("bcd", run_bcd)
             uv.append(timed("consistency", lambda: ops.flow_from_labels(pv, lab, want_yx=False)[1]))
         if directions == 2:
@@ -324,8 +322,24 @@ def main():
                 ach, peak, unit = amount / secs / 1e9, pk["hbm"], "GB/s"
             else:
                 ach, peak, unit = amount / secs / 1e12, pk["tensor"], "TFLOP/s"
-            roof = {"kernel": dom, "bound": kind, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                    "traffic": None, "peak_source": pk["src"], "ms": stages[dom],
+            # per launch, as the contract asks: the dominant stage is a sequence of identical launches
+            n_launch = {"bcd": directions * sweeps * 4, "knn": directions, "daisy": 2, "random": directions,
+                        "consistency": 1}[dom]
+            kname = {"bcd": "bcd_chain_kernel", "knn": "knn_select_kernel (+ re-rank)", "daisy": "daisy kernels",
+                     "random": "random_proposals_kernel", "consistency": "consistency_kernel"}[dom]
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+            if os.path.isfile(tpath):
+                with open(tpath) as f:
+                    for k, v in json.load(f)["kernels"].items():
+                        if k.startswith(kname.split(" ")[0]):
+                            traffic = v["mean_dram_bytes_per_launch"]
+            roof = {"kernel": kname, "stage": dom, "bound": kind, "achieved": ach, "peak": peak, "unit": unit,
+                    "frac": ach / peak, "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu --set full)",
+                    "peak_source": pk["src"] + " (MEASURED_PEAKS.json)", "launches_per_step": n_launch,
+                    "algorithmic_per_launch": amount / n_launch, "ms_per_launch": stages[dom] / n_launch,
+                    "note": "stage time by CUDA events around the stage's C-ABI call on the launching stream"
+                            + ("; includes bcd_sort_kernel once per direction" if dom == "bcd" else ""),
                     "stage_ms": {k: round(v, 4) for k, v in stages.items()},
                     "stage_frac_of_roofline": {
                         k: round((work[k][1] / (v / 1e3) / (1e9 if work[k][0] == "hbm" else 1e12)) /

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libflowb200.so")
 
 OK, EINVAL, EWORKSPACE, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4
-BCD_FP64_F32COST, BCD_FP64_F64COST, BCD_INT32 = 0, 1, 2
+BCD_FP64_F32COST, BCD_FP64_F64COST, BCD_INT32, BCD_INT32_F32COST = 0, 1, 2, 3
 KNN_EXACT_FP64, KNN_TCGEN05 = 0, 1
 
 

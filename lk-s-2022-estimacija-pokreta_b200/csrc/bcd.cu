@@ -11,6 +11,7 @@
 // Arithmetic modes (include/flowb200.h): float64 with the reference's operation order (bit-exact for any
 // data cost) or int32 in units of 2^-S (bit-exact when lcost == 20*m/2^S).
 #include <math_constants.h>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -205,6 +206,16 @@ bcd_sort_kernel(const int32_t* __restrict__ pvec, const int32_t* __restrict__ np
     }
     __syncwarp();
   }
+}
+
+// data term in DP units.  int32 programme on float32 costs: quantised on the fly exactly as flowb200_quantise_costs
+// does, m = rint(lamda * lcost * 2^S) in float64
+template <typename DP, typename CostT>
+__device__ __forceinline__ DP int_cost(CostT c, double lamda, int shift) {
+  if constexpr (sizeof(CostT) == 4 && !std::is_integral<CostT>::value)
+    return (DP)rint(__dmul_rn(__dmul_rn(lamda, (double)c), (double)(1 << shift)));
+  else
+    return (DP)c;
 }
 
 template <typename DP> struct RepT;
@@ -463,7 +474,7 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
           if constexpr (sizeof(DP) == 8) {   // (psi+ + psi-) + lamda*lcost   (:118-120)
             dpv[r] = __dadd_rn((double)(psi_p + psi_m), __dmul_rn(lamda, (double)c[r]));
           } else {
-            dpv[r] = (DP)c[r] + ((psi_p + psi_m) << shift);
+            dpv[r] = int_cost<DP, CostT>(c[r], lamda, shift) + ((psi_p + psi_m) << shift);
           }
         } else {
           const DP m = m_s[run];
@@ -471,7 +482,7 @@ bcd_chain_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cos
             double U = __dadd_rn(__dadd_rn(__dmul_rn(lamda, (double)c[r]), (double)psi_p), (double)psi_m);
             dpv[r] = __dadd_rn(m, U);
           } else {
-            dpv[r] = m + (DP)c[r] + ((psi_p + psi_m) << shift);
+            dpv[r] = m + int_cost<DP, CostT>(c[r], lamda, shift) + ((psi_p + psi_m) << shift);
           }
           bp_chain[(size_t)i * Kpad + orig[r]] = (uint16_t)arg_s[run];
         }
@@ -645,6 +656,10 @@ extern "C" int flowb200_bcd(const int32_t* pvec, const void* cost, const int32_t
     case FLOWB200_BCD_FP64_F64COST:
       return launch_sweeps<double, double>(pvec, static_cast<const double*>(cost), nprop, labels, H, W, K, lamda, tpsi,
                                            0, sweeps, labels_per_sweep, bp, order, stream);
+    case FLOWB200_BCD_INT32_F32COST:
+      if (cost_shift < 0 || cost_shift > 14) return FLOWB200_EINVAL;
+      return launch_sweeps<int32_t, float>(pvec, static_cast<const float*>(cost), nprop, labels, H, W, K, lamda, tpsi,
+                                           cost_shift, sweeps, labels_per_sweep, bp, order, stream);
     case FLOWB200_BCD_INT32:
       if (cost_shift < 0 || cost_shift > 14) return FLOWB200_EINVAL;
       return launch_sweeps<int32_t, int32_t>(pvec, static_cast<const int32_t*>(cost), nprop, labels, H, W, K, lamda,

@@ -496,15 +496,17 @@ template <int KC>
 __device__ __forceinline__ void emit_proposal(const KnnTcGeom& g, const float* __restrict__ q, const float* __restrict__ desc_tgt,
                                               int qx, int qy, int ci, int cj, int blk, int rank, int idx,
                                               int32_t* __restrict__ pvec, float* __restrict__ lcost,
-                                              int32_t* __restrict__ knn_idx) {
+                                              int32_t* __restrict__ knn_idx, unsigned long long* __restrict__ best64) {
   const int ty = cj * g.cellh + idx / g.cellw, tx = ci * g.cellw + idx % g.cellw;
   const float* t = desc_tgt + ((size_t)ty * g.W + tx) * kDescDim;
   const float s = sum68_numpy_order([&](int d) { return fabsf(__fsub_rn(q[d], t[d])); });
   const size_t pix = (size_t)qy * g.W + qx;
   const int slot = KC * blk + rank;
   pvec[pix * g.K + slot] = pack_vec(ty - qy, tx - qx);
-  lcost[pix * g.K + slot] = s < g.tphi ? s : g.tphi;
+  const float c = s < g.tphi ? s : g.tphi;
+  lcost[pix * g.K + slot] = c;
   if (knn_idx) knn_idx[(pix * g.nblk + blk) * KC + rank] = idx;
+  atomicMin(best64 + pix, ((unsigned long long)__float_as_uint(c) << 32) | (uint32_t)slot);
 }
 
 // One pass over a (query, target) descriptor pair:
@@ -549,7 +551,8 @@ template <int KC>
 __global__ void __launch_bounds__(256, 4)
 knn_rerank_kernel(const float* __restrict__ desc_src, const float* __restrict__ desc_tgt, KnnTcGeom g,
                   const uint16_t* __restrict__ cand, const uint8_t* __restrict__ cand_cnt, int32_t* __restrict__ pvec,
-                  float* __restrict__ lcost, int32_t* __restrict__ knn_idx, int32_t* __restrict__ fb_list,
+                  float* __restrict__ lcost, int32_t* __restrict__ knn_idx, int32_t* __restrict__ nprop,
+                  unsigned long long* __restrict__ best64, int32_t* __restrict__ fb_list,
                   int32_t* __restrict__ fb_count, int fb_cap) {
   const int sub = threadIdx.x & 15;
   const size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
@@ -560,6 +563,9 @@ knn_rerank_kernel(const float* __restrict__ desc_src, const float* __restrict__ 
   cell_range(qx, g.cellw, g.ncellx, g.R, &cimin, &cimax);
   cell_range(qy, g.cellh, g.ncelly, g.R, &cjmin, &cjmax);
   const float* qp = desc_src + pix * kDescDim;
+  // running (cost, slot) minimum of this lane's proposals: bestlabels = first strict argmin (:181-184) = the
+  // lexicographic minimum; costs are >= 0, so their float bit patterns order like the values
+  unsigned long long bkey = ((unsigned long long)__float_as_uint(FLOWB200_UNUSED_COST) << 32);
   int blk = 0;
   for (int ci = cimin; ci <= cimax; ++ci) {
     for (int cj = cjmin; cj <= cjmax; ++cj, ++blk) {
@@ -639,17 +645,45 @@ knn_rerank_kernel(const float* __restrict__ desc_src, const float* __restrict__ 
       if (sub < n && rank0 < KC) {
         const int r = id0 / g.cellw, cc = id0 - r * g.cellw;
         pvec[obase + rank0] = pack_vec(ty0 + r - qy, tx0 + cc - qx);
-        lcost[obase + rank0] = co0 < g.tphi ? co0 : g.tphi;       // min(tphi, sum) (:178-180)
+        const float cc0 = co0 < g.tphi ? co0 : g.tphi;            // min(tphi, sum) (:178-180)
+        lcost[obase + rank0] = cc0;
+        const unsigned long long k0 = ((unsigned long long)__float_as_uint(cc0) << 32) | (uint32_t)(KC * blk + rank0);
+        if (k0 < bkey) bkey = k0;
         if (knn_idx) knn_idx[(pix * g.nblk + blk) * KC + rank0] = id0;
       }
       if (two && 16 + sub < n && rank1 < KC) {
         const int r = id1 / g.cellw, cc = id1 - r * g.cellw;
         pvec[obase + rank1] = pack_vec(ty0 + r - qy, tx0 + cc - qx);
-        lcost[obase + rank1] = co1 < g.tphi ? co1 : g.tphi;
+        const float cc1 = co1 < g.tphi ? co1 : g.tphi;
+        lcost[obase + rank1] = cc1;
+        const unsigned long long k1 = ((unsigned long long)__float_as_uint(cc1) << 32) | (uint32_t)(KC * blk + rank1);
+        if (k1 < bkey) bkey = k1;
         if (knn_idx) knn_idx[(pix * g.nblk + blk) * KC + rank1] = id1;
       }
     }
   }
+  // what finish_nn does for the float64 path: nprop, fills of the unused slots, and the pre-BCD best label
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(gmask, bkey, off, 16);
+    if (o < bkey) bkey = o;
+  }
+  const int nn = KC * blk;
+  if (sub == 0) {
+    nprop[pix] = nn;
+    best64[pix] = bkey;      // brute-forced tasks fold their proposals in with atomicMin (knn_fallback_kernel)
+  }
+  for (int sl = nn + sub; sl < g.K; sl += 16) {
+    pvec[pix * g.K + sl] = -1;
+    lcost[pix * g.K + sl] = FLOWB200_UNUSED_COST;
+  }
+  if (knn_idx)
+    for (int sl = nn + sub; sl < g.nblk * KC; sl += 16) knn_idx[pix * (size_t)(g.nblk * KC) + sl] = -1;
+}
+
+__global__ void labels_from_best_kernel(const unsigned long long* __restrict__ best64, int32_t* __restrict__ labels, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) labels[i] = (int32_t)(best64[i] & 0xffffffffu);
 }
 
 // brute force for the (rare) tasks whose candidate lists overflowed: one block per task
@@ -657,7 +691,8 @@ template <int KC>
 __global__ void __launch_bounds__(128)
 knn_fallback_kernel(const float* __restrict__ desc_src, const float* __restrict__ desc_tgt, KnnTcGeom g,
                     const int32_t* __restrict__ fb_list, const int32_t* __restrict__ fb_count, int fb_cap,
-                    int32_t* __restrict__ pvec, float* __restrict__ lcost, int32_t* __restrict__ knn_idx) {
+                    int32_t* __restrict__ pvec, float* __restrict__ lcost, int32_t* __restrict__ knn_idx,
+                    unsigned long long* __restrict__ best64) {
   extern __shared__ double fb_d[];       // [T]
   __shared__ double red_d[4];
   __shared__ int red_i[4];
@@ -707,7 +742,7 @@ knn_fallback_kernel(const float* __restrict__ desc_src, const float* __restrict_
             bi = red_i[w];
           }
         fb_d[bi] = CUDART_INF;
-        emit_proposal<KC>(g, q, desc_tgt, qx, qy, ci, cj, blk, rank, bi, pvec, lcost, knn_idx);
+        emit_proposal<KC>(g, q, desc_tgt, qx, qy, ci, cj, blk, rank, bi, pvec, lcost, knn_idx, best64);
       }
       __syncthreads();
     }
@@ -767,7 +802,7 @@ static KnnTcGeom make_tc_geom(const flowb200_params* p) {
 }
 
 struct TcLayout {
-  size_t q16, t16, qinfo, cellinfo, cand, cnt, fb_list, fb_count, total;
+  size_t q16, t16, qinfo, cellinfo, cand, cnt, best, fb_list, fb_count, total;
   int grid, fb_cap;
 };
 
@@ -785,6 +820,7 @@ static TcLayout tc_layout(const flowb200_params* p) {
   L.cellinfo = take(ncell * 4 * sizeof(int));
   L.cand = take(n * g.nblk * kCand * sizeof(uint16_t));
   L.cnt = take(n * g.nblk);
+  L.best = take(n * sizeof(unsigned long long));
   L.fb_list = take((size_t)L.fb_cap * 2 * sizeof(int32_t));
   L.fb_count = take(256);
   L.total = off;
@@ -801,7 +837,8 @@ bool knn_tc_supported(const flowb200_params* p) {
 
 template <int KC>
 static int run_tc(const float* desc_src, const float* desc_tgt, const flowb200_params* p, const KnnTcGeom& g,
-                  const TcLayout& L, char* ws, int32_t* pvec, float* lcost, int32_t* knn_idx, int32_t* stats,
+                  const TcLayout& L, char* ws, int32_t* pvec, float* lcost, int32_t* nprop, int32_t* labels,
+                  int32_t* knn_idx, int32_t* stats,
                   float* dbg_scores, cudaStream_t stream) {
   const size_t n = (size_t)g.H * g.W;
   const int ncell = g.ncellx * g.ncelly;
@@ -813,6 +850,7 @@ static int run_tc(const float* desc_src, const float* desc_tgt, const flowb200_p
   uint8_t* cnt = reinterpret_cast<uint8_t*>(ws + L.cnt);
   int32_t* fb_list = reinterpret_cast<int32_t*>(ws + L.fb_list);
   int32_t* fb_count = reinterpret_cast<int32_t*>(ws + L.fb_count);
+  unsigned long long* best64 = reinterpret_cast<unsigned long long*>(ws + L.best);
 
   FB_CUDA_CHECK(cudaMemsetAsync(cellinfo, 0, (size_t)ncell * 4 * sizeof(int), stream));
   FB_CUDA_CHECK(cudaMemsetAsync(fb_count, 0, 8 * sizeof(int32_t), stream));
@@ -834,13 +872,16 @@ static int run_tc(const float* desc_src, const float* desc_tgt, const flowb200_p
   FB_LAUNCH_CHECK();
 
   const unsigned rgrid = (unsigned)((n * 16 + 255) / 256);
-  knn_rerank_kernel<KC><<<rgrid, 256, 0, stream>>>(desc_src, desc_tgt, g, cand, cnt, pvec, lcost, knn_idx, fb_list,
-                                                    fb_count, L.fb_cap);
+  knn_rerank_kernel<KC><<<rgrid, 256, 0, stream>>>(desc_src, desc_tgt, g, cand, cnt, pvec, lcost, knn_idx, nprop, best64,
+                                                    fb_list, fb_count, L.fb_cap);
   FB_LAUNCH_CHECK();
   auto fkern = knn_fallback_kernel<KC>;
   const size_t fsmem = (size_t)g.T * sizeof(double);
   if (fsmem > 48 * 1024) FB_CUDA_CHECK(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-  fkern<<<4 * kNumSMs, 128, fsmem, stream>>>(desc_src, desc_tgt, g, fb_list, fb_count, L.fb_cap, pvec, lcost, knn_idx);
+  fkern<<<4 * kNumSMs, 128, fsmem, stream>>>(desc_src, desc_tgt, g, fb_list, fb_count, L.fb_cap, pvec, lcost, knn_idx,
+                                                   best64);
+  FB_LAUNCH_CHECK();
+  labels_from_best_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(best64, labels, (int)n);
   FB_LAUNCH_CHECK();
   // stats: {fallback tasks, collect-list overflows, candidate-list overflows, -, sum candidates, sum collected}
   if (stats) FB_CUDA_CHECK(cudaMemcpyAsync(stats, fb_count, 6 * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
@@ -849,7 +890,7 @@ static int run_tc(const float* desc_src, const float* desc_tgt, const flowb200_p
 }
 
 int knn_tc_dispatch(const float* desc_src, const float* desc_tgt, const flowb200_params* p, int32_t* pvec, float* lcost,
-                    int32_t* knn_idx, int32_t* stats, float* dbg_scores, void* workspace, size_t workspace_bytes,
+                    int32_t* nprop, int32_t* labels, int32_t* knn_idx, int32_t* stats, float* dbg_scores, void* workspace, size_t workspace_bytes,
                     cudaStream_t stream) {
   if (!knn_tc_supported(p)) return FLOWB200_EUNSUPPORTED;
   const TcLayout L = tc_layout(p);
@@ -857,9 +898,12 @@ int knn_tc_dispatch(const float* desc_src, const float* desc_tgt, const flowb200
   const KnnTcGeom g = make_tc_geom(p);
   char* ws = static_cast<char*>(workspace);
   switch (p->k_cell) {
-    case 5: return run_tc<5>(desc_src, desc_tgt, p, g, L, ws, pvec, lcost, knn_idx, stats, dbg_scores, stream);
-    case 10: return run_tc<10>(desc_src, desc_tgt, p, g, L, ws, pvec, lcost, knn_idx, stats, dbg_scores, stream);
-    case 12: return run_tc<12>(desc_src, desc_tgt, p, g, L, ws, pvec, lcost, knn_idx, stats, dbg_scores, stream);
+    case 5: return run_tc<5>(desc_src, desc_tgt, p, g, L, ws, pvec, lcost, nprop, labels, knn_idx, stats, dbg_scores,
+                               stream);
+    case 10: return run_tc<10>(desc_src, desc_tgt, p, g, L, ws, pvec, lcost, nprop, labels, knn_idx, stats, dbg_scores,
+                               stream);
+    case 12: return run_tc<12>(desc_src, desc_tgt, p, g, L, ws, pvec, lcost, nprop, labels, knn_idx, stats, dbg_scores,
+                               stream);
     default: return FLOWB200_EUNSUPPORTED;
   }
 }
@@ -877,15 +921,19 @@ int knn_tc_debug_scores(const float* desc_src, const float* desc_tgt, const flow
   if (!scores) return FLOWB200_OK;
   if (workspace_bytes < L.total) return FLOWB200_EWORKSPACE;
   const size_t n = (size_t)g.H * g.W;   // the proposals of this diagnostic run go to a throw-away allocation
-  int32_t* pvec = nullptr;
+  int32_t *pvec = nullptr, *np_ = nullptr, *lb_ = nullptr;
   float* lcost = nullptr;
   FB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&pvec), n * g.K * sizeof(int32_t)));
   FB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&lcost), n * g.K * sizeof(float)));
-  int rc = knn_tc_dispatch(desc_src, desc_tgt, p, pvec, lcost, nullptr, nullptr, scores, workspace, workspace_bytes,
-                           stream);
+  FB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&np_), n * sizeof(int32_t)));
+  FB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&lb_), n * sizeof(int32_t)));
+  int rc = knn_tc_dispatch(desc_src, desc_tgt, p, pvec, lcost, np_, lb_, nullptr, nullptr, scores, workspace,
+                           workspace_bytes, stream);
   cudaStreamSynchronize(stream);
   cudaFree(pvec);
   cudaFree(lcost);
+  cudaFree(np_);
+  cudaFree(lb_);
   return rc;
 }
 

@@ -40,7 +40,7 @@ static AuxStream* aux_stream() {
 }
 
 struct PairLayout {
-  size_t desc[2], daisy_ws, pvec[2], lcost[2], mcost[2], nprop[2], labels[2], uvv[2], bcd_ws[2], knn_ws[2], total;
+  size_t desc[2], daisy_ws, pvec[2], lcost[2], nprop[2], labels[2], uvv[2], bcd_ws[2], knn_ws[2], total;
 };
 
 static PairLayout pair_layout(const flowb200_params* p) {
@@ -58,7 +58,6 @@ static PairLayout pair_layout(const flowb200_params* p) {
   for (int d = 0; d < 2; ++d) {
     L.pvec[d] = take(n * K * sizeof(int32_t));
     L.lcost[d] = take(n * K * sizeof(float));
-    L.mcost[d] = take(p->bcd_mode == FLOWB200_BCD_INT32 ? n * K * sizeof(int32_t) : 0);
     L.nprop[d] = take(n * sizeof(int32_t));
     L.labels[d] = take(n * sizeof(int32_t));
     L.uvv[d] = take(n * 3 * sizeof(float));
@@ -109,16 +108,12 @@ static int run_direction(const flowb200_params* p, const PairLayout& L, char* ws
   if (rc) return rc;
   rc = flowb200_random_proposals(src, tgt, p, pvec, lcost, nprop, labels, nullptr, seed + (uint64_t)d, stream);
   if (rc) return rc;
-  const void* cost = lcost;
-  if (p->bcd_mode == FLOWB200_BCD_INT32) {
-    int32_t* m = reinterpret_cast<int32_t*>(ws + L.mcost[d]);
-    rc = flowb200_quantise_costs(lcost, m, n * p->maxnprop, p->lamda, p->cost_shift, stream);
-    if (rc) return rc;
-    cost = m;
-  } else if (p->bcd_mode != FLOWB200_BCD_FP64_F32COST) {
-    return FLOWB200_EINVAL;   // the pipeline produces float32 costs
-  }
-  rc = flowb200_bcd(pvec, cost, nprop, labels, p->H, p->W, p->maxnprop, p->bcd_mode, p->lamda, p->tpsi, p->cost_shift,
+  // the pipeline produces float32 costs: the int32 programme quantises them on the fly
+  int mode = p->bcd_mode;
+  if (mode == FLOWB200_BCD_INT32) mode = FLOWB200_BCD_INT32_F32COST;
+  if (mode != FLOWB200_BCD_INT32_F32COST && mode != FLOWB200_BCD_FP64_F32COST) return FLOWB200_EINVAL;
+  (void)n;
+  rc = flowb200_bcd(pvec, lcost, nprop, labels, p->H, p->W, p->maxnprop, mode, p->lamda, p->tpsi, p->cost_shift,
                     sweeps, nullptr, ws + L.bcd_ws[d], flowb200_bcd_workspace_bytes(p->H, p->W, p->maxnprop), stream);
   if (rc) return rc;
   return flowb200_flow_from_labels(pvec, labels, p->H, p->W, p->maxnprop, nullptr,

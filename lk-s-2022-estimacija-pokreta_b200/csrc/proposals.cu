@@ -357,8 +357,8 @@ int finish_nn(const flowb200_params* p, int32_t* pvec, float* lcost, int32_t* np
 size_t knn_tc_workspace_bytes(const flowb200_params* p);
 bool knn_tc_supported(const flowb200_params* p);
 int knn_tc_dispatch(const float* desc_src, const float* desc_tgt, const flowb200_params* p, int32_t* pvec, float* lcost,
-                    int32_t* knn_idx, int32_t* stats, float* dbg_scores, void* workspace, size_t workspace_bytes,
-                    cudaStream_t stream);
+                    int32_t* nprop, int32_t* labels, int32_t* knn_idx, int32_t* stats, float* dbg_scores, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream);
 int knn_tc_debug_scores(const float* desc_src, const float* desc_tgt, const flowb200_params* p, float* scores,
                         int32_t* geom_out_host, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
@@ -389,7 +389,9 @@ extern "C" int flowb200_knn_proposals(const float* desc_src, const float* desc_t
   if (!desc_src || !desc_tgt || !pvec || !lcost || !nprop || !labels) return FLOWB200_EINVAL;
   if (p->knn_mode == FLOWB200_KNN_TCGEN05) {
     if (!workspace) return FLOWB200_EINVAL;
-    rc = knn_tc_dispatch(desc_src, desc_tgt, p, pvec, lcost, knn_idx, stats, nullptr, workspace, workspace_bytes, stream);
+    // the tensor-core path also writes nprop, the unused-slot fills and bestlabels
+    return knn_tc_dispatch(desc_src, desc_tgt, p, pvec, lcost, nprop, labels, knn_idx, stats, nullptr, workspace,
+                           workspace_bytes, stream);
   } else if (p->knn_mode == FLOWB200_KNN_EXACT_FP64) {
     rc = knn_exact_dispatch(desc_src, desc_tgt, p, pvec, lcost, knn_idx, stream);
   } else {

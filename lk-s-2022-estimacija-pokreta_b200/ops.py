@@ -120,7 +120,7 @@ def quantise_costs(lcost, lamda=0.05, shift=12):
 
 
 _BCD_COST_DTYPE = {_lib.BCD_FP64_F32COST: torch.float32, _lib.BCD_FP64_F64COST: torch.float64,
-                   _lib.BCD_INT32: torch.int32}
+                   _lib.BCD_INT32: torch.int32, _lib.BCD_INT32_F32COST: torch.float32}
 
 
 def bcd(pvec, cost, nprop, labels, sweeps, mode=_lib.BCD_FP64_F32COST, lamda=0.05, tpsi=8, cost_shift=12,

@@ -289,6 +289,19 @@ def test_bcd_vs_oracle_random(H, W, K):
         assert np.array_equal(snaps[0], want[0]) and np.array_equal(snaps[1], want[1]), mode
 
 
+def test_bcd_int32_on_float_costs_equals_quantise_then_int32():
+    ops, ioc, lib = pkg("ops"), pkg("io_contract"), pkg("_lib")
+    z = load_case("pair_a")
+    pvec = dev(ioc.pack_proposals(z["b0_proposals"]))
+    nprop = dev(z["b0_nprop"], torch.int32)
+    lc = dev(z["b0_lcosts"], torch.float32)
+    a = dev(z["b0_labels00"], torch.int32)
+    b = a.clone()
+    ops.bcd(pvec, ops.quantise_costs(lc, 0.05, 12), nprop, a, 2, mode=lib.BCD_INT32, cost_shift=12)
+    ops.bcd(pvec, lc, nprop, b, 2, mode=lib.BCD_INT32_F32COST, cost_shift=12)
+    assert torch.equal(a, b)
+
+
 def test_quantise_costs():
     ops = pkg("ops")
     rng = np.random.default_rng(0)
