@@ -115,9 +115,22 @@ def consistency_cases():
     np.savez_compressed(os.path.join(OUT, "consistency.npz"), **data)
 
 
+def parovi_case():
+    """The reference's napravi_parove.parovi on the 'real' consistency output -> tests/golden/parovi_real.txt."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_parovi", os.path.join(rh.REF, "napravi_parove.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    z = np.load(os.path.join(OUT, "consistency.npz"))
+    d = tempfile.mkdtemp()
+    np.save(os.path.join(d, "f.npy"), z["real_out"])
+    mod.parovi(os.path.join(d, "f.npy"), os.path.join(OUT, "parovi_real.txt"))
+
+
 if __name__ == "__main__":
     assert rh.available(), "reference source not found"
     consistency_cases()
+    parovi_case()
     stage_case("pair_a", 40, 48, 12, 10, pair=3, sweeps=2, seed=5, both_dirs=True, thresholds=(10, 2))
     stage_case("pair_b", 44, 50, 12, 10, pair=7, sweeps=1, seed=9, both_dirs=False)
     bcd_quantised_case("bcd_q12", "pair_a", sweeps=3, shift=12)

@@ -103,3 +103,17 @@ def test_file_names_match_reference_contract():
     assert ioc.stage1_file(6, 0, "nprop") == "Daisy output slike 106 backward=0 nprop.npy"
     a, b = ioc.image_paths(6, 1)
     assert a.endswith("image_2/000106_11.png") and b.endswith("image_2/000106_10.png")
+
+
+def test_parovi_match_list_is_byte_identical(tmp_path):
+    """napravi_parove.parovi (EpicFlow match list) against the text the reference's own module wrote for the
+    'real' consistency fixture (tests/golden/parovi_real.txt, generated in the build container)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import napravi_parove
+    from helpers import load_npz, GOLDEN
+    z = load_npz("consistency")
+    np.save(tmp_path / "f.npy", z["real_out"])
+    napravi_parove.parovi(str(tmp_path / "f.npy"), str(tmp_path / "p.txt"))
+    with open(os.path.join(GOLDEN, "parovi_real.txt")) as f:
+        assert (tmp_path / "p.txt").read_text() == f.read()
