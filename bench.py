@@ -345,6 +345,15 @@ def main():
                         k: round((work[k][1] / (v / 1e3) / (1e9 if work[k][0] == "hbm" else 1e12)) /
                                  (pk["hbm"] if work[k][0] == "hbm" else pk["tensor"]), 5) if v > 0 else None
                         for k, v in stages.items()}}
+        # accuracy on the synthetic pair (known ground-truth flow), visualization.errorImage's definition, untimed
+        gt = torch.from_numpy(synth.gt_uvv(pairs[0][2])).cuda()
+        chk, raw_f, _ = ops.flow_pair(dev_pairs[0][0], dev_pairs[0][1], p, sweeps, directions, seed=0, bcd_mode=bcd_mode,
+                                      want_raw=True, workspace=ws)
+        e_raw, e_chk = ops.epe(raw_f, gt), ops.epe(chk, gt)
+        accuracy = {"epe_px_forward_raw": e_raw[0], "outlier_pct_forward_raw": e_raw[1],
+                    "epe_px_after_consistency": e_chk[0], "outlier_pct_after_consistency": e_chk[1],
+                    "kept_frac_after_consistency": e_chk[2] / max(1, e_raw[2]),
+                    "definition": "visualization.py:128-152 (EPE > 3 px = outlier), vs the synthetic ground truth"}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             r = cpu_sample(p, sweeps, directions, steps=2)
@@ -359,7 +368,8 @@ def main():
                            "l2": "per-step working set (proposals+costs, >1 GB) exceeds L2; 2 pairs cycled"},
                 "e2e": {"value": e2e_mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * p.H * p.W * 3,
                         "d2h_bytes_per_step": p.H * p.W * 12},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "accuracy": accuracy}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

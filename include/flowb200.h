@@ -144,6 +144,12 @@ int flowb200_flow_from_labels(const int32_t* pvec, const int32_t* labels, int H,
 int flowb200_consistency(float* flow1, const float* flow2, int A, int B, float tresh,
                          int a0, int a1, int b0, int b1, flowb200_stream_t stream);
 
+/* ---- metric: visualization.errorImage (visualization.py:128-152), the EPE definition of the benchmark ----
+ * test/gt: float32 [H][W][3] = (u, v, valid).  out3 (device float64[3]) = {sum of end-point errors over pixels valid
+ * in both, number of them with error > abs_thresh (3.0 in the reference), number of pixels valid in both}. */
+int flowb200_epe(const float* test_uvv, const float* gt_uvv, int H, int W, float abs_thresh, double* out3,
+                 flowb200_stream_t stream);
+
 /* ---- whole path, device resident: two DAISYs, per direction kNN + random proposals + `sweeps` BCD
  *      sweeps, then the forward/backward check.  bgr0/bgr1: uint8 [H][W][3].
  * out_fwd: float32 [H][W][3] checked forward field (sparse_field.npy layout); out_fwd_raw / out_bwd_raw

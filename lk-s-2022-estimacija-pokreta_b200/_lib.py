@@ -50,6 +50,7 @@ SYMBOLS = {
                                C.c_int, _P, _P, C.c_size_t, _P]),
     "flowb200_flow_from_labels": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "flowb200_consistency": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "flowb200_epe": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P]),
     "flowb200_pair_workspace_bytes": (C.c_size_t, [_PP]),
     "flowb200_flow_pair": (C.c_int, [_P, _P, _PP, C.c_int, C.c_int, C.c_uint64, _P, _P, _P, _P, C.c_size_t, _P]),
     "flowb200_ctx_create": (_P, [_PP]),

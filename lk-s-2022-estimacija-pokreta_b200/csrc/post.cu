@@ -59,9 +59,47 @@ __global__ void consistency_kernel(float* __restrict__ f1, const float* __restri
   }
 }
 
+// visualization.errorImage (visualization.py:128-152): over pixels valid in both fields, f_err = sqrt(dfu^2 + dfv^2)
+// in float32; accumulates sum(f_err), #(f_err > abs_thresh), #valid in float64.
+__global__ void epe_kernel(const float* __restrict__ test, const float* __restrict__ gt, int n_pix, float abs_thresh,
+                           double* __restrict__ out) {
+  double s = 0.0, no = 0.0, nv = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += gridDim.x * blockDim.x) {
+    const float* t = test + 3 * (size_t)i;
+    const float* g = gt + 3 * (size_t)i;
+    if (t[2] > 0.5f && g[2] > 0.5f) {
+      const float dfu = __fsub_rn(t[0], g[0]), dfv = __fsub_rn(t[1], g[1]);
+      const float e = __fsqrt_rn(__fadd_rn(__fmul_rn(dfu, dfu), __fmul_rn(dfv, dfv)));
+      s += (double)e;
+      no += e > abs_thresh ? 1.0 : 0.0;
+      nv += 1.0;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    no += __shfl_xor_sync(0xffffffffu, no, off);
+    nv += __shfl_xor_sync(0xffffffffu, nv, off);
+  }
+  if ((threadIdx.x & 31) == 0 && nv > 0.0) {
+    atomicAdd(out, s);
+    atomicAdd(out + 1, no);
+    atomicAdd(out + 2, nv);
+  }
+}
+
 }  // namespace flowb200
 
 using namespace flowb200;
+
+extern "C" int flowb200_epe(const float* test_uvv, const float* gt_uvv, int H, int W, float abs_thresh, double* out3,
+                            flowb200_stream_t stream) {
+  if (!test_uvv || !gt_uvv || !out3 || H <= 0 || W <= 0) return FLOWB200_EINVAL;
+  FB_CUDA_CHECK(cudaMemsetAsync(out3, 0, 3 * sizeof(double), stream));
+  epe_kernel<<<kNumSMs * 4, 256, 0, stream>>>(test_uvv, gt_uvv, H * W, abs_thresh, out3);
+  FB_LAUNCH_CHECK();
+  return FLOWB200_OK;
+}
 
 extern "C" int flowb200_flow_from_labels(const int32_t* pvec, const int32_t* labels, int H, int W, int K,
                                          double* flow_yx, float* uvv, flowb200_stream_t stream) {

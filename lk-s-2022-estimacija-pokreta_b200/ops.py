@@ -163,6 +163,19 @@ def consistency(flow1, flow2, tresh, region=None):
     return flow1
 
 
+def epe(test_uvv, gt_uvv, abs_thresh=3.0):
+    """visualization.errorImage (visualization.py:128-152): (mean EPE, outlier %, n_valid) over pixels valid in both."""
+    lib = _lib.load()
+    H, W, _ = test_uvv.shape
+    out = torch.empty(3, dtype=torch.float64, device=test_uvv.device)
+    _lib.check(lib.flowb200_epe(_ptr(test_uvv, torch.float32), _ptr(gt_uvv, torch.float32), H, W, float(abs_thresh),
+                                _ptr(out), _stream()), "flowb200_epe")
+    s, no, nv = out.tolist()
+    if nv == 0:
+        return float("nan"), float("nan"), 0
+    return s / nv, 100.0 * no / nv, int(nv)
+
+
 def flow_pair(bgr0, bgr1, p: FlowParams, sweeps, directions=2, seed=0, bcd_mode=_lib.BCD_FP64_F32COST,
               want_raw=False, workspace=None):
     """Whole device-resident path.  Returns checked forward field float32 (H,W,3) (and raw fwd/bwd fields)."""

@@ -312,6 +312,20 @@ def test_quantise_costs():
     assert np.array_equal(m, want)
 
 
+def test_epe_metric_matches_error_image():
+    from oracle import epe as oepe
+    ops = pkg("ops")
+    rng = np.random.default_rng(2)
+    H, W = 77, 123
+    t = np.concatenate([rng.normal(0, 5, (H, W, 2)), rng.random((H, W, 1)) > 0.2], -1).astype(np.float32)
+    g = np.concatenate([t[..., :2] + rng.normal(0, 2, (H, W, 2)), rng.random((H, W, 1)) > 0.1], -1).astype(np.float32)
+    want = oepe.error_image(t, g)
+    got = ops.epe(dev(t), dev(g))
+    assert got[2] == want[2]
+    assert abs(got[0] - want[0]) <= 1e-5 * want[0] and abs(got[1] - want[1]) < 1e-9       # float64 vs float32 averaging
+    assert ops.epe(dev(t * 0), dev(g * 0))[2] == 0
+
+
 # ---------------------------------------------------------------- whole path
 def test_pipeline_matches_stagewise_and_oracle():
     """flow_pair (device resident) == the stages called one by one; EPE vs the oracle pipeline <= 0.01 px."""
