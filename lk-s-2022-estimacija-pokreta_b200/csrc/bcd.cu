@@ -11,35 +11,12 @@
 // Arithmetic modes (include/flowb200.h): float64 with the reference's operation order (bit-exact for any
 // data cost) or int32 in units of 2^-S (bit-exact when lcost == 20*m/2^S).
 #include <math_constants.h>
+#include <stdlib.h>
 #include <type_traits>
 
-#include "common.cuh"
+#include "bcd_common.cuh"
 
 namespace flowb200 {
-
-struct ChainGeom {
-  int sy, sx, ystep, xstep, len;
-};
-
-__device__ __forceinline__ ChainGeom chain_geom(int phase, int c, int H, int W) {
-  ChainGeom g;
-  switch (phase) {
-    case 0: g = {0, 2 * c, 1, 0, H}; break;           // even columns, downwards   (:265-266)
-    case 1: g = {2 * c, W - 1, 0, -1, W}; break;      // even rows, right to left  (:270-271)
-    case 2: g = {H - 1, 2 * c + 1, -1, 0, H}; break;  // odd columns, upwards      (:273-274)
-    default: g = {2 * c + 1, 0, 0, 1, W}; break;      // odd rows, left to right   (:276-277)
-  }
-  return g;
-}
-
-static inline int phase_chains(int phase, int H, int W) {
-  switch (phase) {
-    case 0: return (W + 1) / 2;
-    case 1: return (H + 1) / 2;
-    case 2: return W / 2;
-    default: return H / 2;
-  }
-}
 
 template <typename DP>
 struct DpOps;
@@ -90,19 +67,10 @@ __device__ __forceinline__ void warp_argmin(DP& val, int& idx) {
 //     previous pixel's per-leader arrays.
 // The hash only prunes: membership is always decided by the exact L1 test, and ties are resolved to the lowest
 // ORIGINAL label index as in the reference (np.argmin), so labels are bit-identical to the dense evaluation.
-constexpr int kHashY = 16, kHashX = 64, kHashSize = kHashY * kHashX;
 // per-pixel order entry: [0,10) original label, [10,20) leader number of the run, 20 leader, 21 first leader of
 // its bucket, 22 last leader of its bucket, [23,32) run length - 1 (leaders only)
 constexpr uint32_t kOrdLeader = 1u << 20, kOrdBStart = 1u << 21, kOrdBEnd = 1u << 22;
 
-// bucket coordinates are offset and clamped (not wrapped) so that buckets adjacent in x have consecutive keys:
-// the leaders of three x-adjacent buckets form ONE contiguous range.  Clamping merges far-away buckets into the
-// border ones, which is harmless because membership is always decided by the exact L1 test.
-__device__ __forceinline__ int bkt_y(int b) { return min(max(b + kHashY / 2, 0), kHashY - 1); }
-__device__ __forceinline__ int bkt_x(int b) { return min(max(b + kHashX / 2, 0), kHashX - 1); }
-__device__ __forceinline__ int bucket_key(int32_t v, int bshift) {
-  return (bkt_y(vec_dy(v) >> bshift) << 6) | bkt_x(vec_dx(v) >> bshift);
-}
 constexpr uint32_t kRngEmpty = 0x0000FFFFu;   // first = 0xFFFF, last+1 = 0
 
 // stable counting sort of idx_in[0..n) by key(idx) into idx_out (one warp; cnt has nkeys + nkeys/32 entries:
@@ -626,11 +594,23 @@ __global__ void quantise_costs_kernel(const float* __restrict__ lcost, int32_t* 
 
 using namespace flowb200;
 
-extern "C" size_t flowb200_bcd_workspace_bytes(int H, int W, int K) {
-  if (H <= 0 || W <= 0 || K <= 0) return 0;
+static size_t legacy_workspace_bytes(int H, int W, int K) {
   size_t Kpad = (size_t)(K + 31) / 32 * 32;
   size_t col = (size_t)((W + 1) / 2) * H, row = (size_t)((H + 1) / 2) * W;
   return align_up((col > row ? col : row) * Kpad * sizeof(uint16_t)) + align_up((size_t)H * W * K * sizeof(uint32_t));
+}
+
+// The int32 programme runs on compiled K-sets (bcd_ksets.cu) unless FLOWB200_BCD_LEGACY is set in the environment
+// (or tpsi > 8); the float64 modes always run the implementation in this file.
+static bool use_ksets(int tpsi) {
+  static const bool legacy = getenv("FLOWB200_BCD_LEGACY") != nullptr;
+  return !legacy && tpsi >= 1 && tpsi <= 8;
+}
+
+extern "C" size_t flowb200_bcd_workspace_bytes(int H, int W, int K) {
+  if (H <= 0 || W <= 0 || K <= 0) return 0;
+  const size_t a = legacy_workspace_bytes(H, W, K), b = ksets_workspace_bytes(H, W, K);
+  return a > b ? a : b;
 }
 
 extern "C" int flowb200_bcd(const int32_t* pvec, const void* cost, const int32_t* nprop, int32_t* labels, int H, int W,
@@ -640,7 +620,17 @@ extern "C" int flowb200_bcd(const int32_t* pvec, const void* cost, const int32_t
   if (!pvec || !cost || !nprop || !labels || !workspace) return FLOWB200_EINVAL;
   if (H <= 0 || W <= 0 || K <= 0 || K > 512 || sweeps < 0 || tpsi < 0) return FLOWB200_EINVAL;
   if (H > 16384 || W > 16384) return FLOWB200_EINVAL;
-  if (workspace_bytes < flowb200_bcd_workspace_bytes(H, W, K)) return FLOWB200_EWORKSPACE;
+  const bool int_mode = bcd_mode == FLOWB200_BCD_INT32 || bcd_mode == FLOWB200_BCD_INT32_F32COST;
+  if (int_mode && use_ksets(tpsi)) {
+    // any workspace that holds the fixed part is accepted: records that do not fit are evaluated densely
+    if (cost_shift < 0 || cost_shift > 14) return FLOWB200_EINVAL;
+    if (bcd_mode == FLOWB200_BCD_INT32)
+      return launch_sweeps_ksets<int32_t>(pvec, static_cast<const int32_t*>(cost), nprop, labels, H, W, K, lamda, tpsi,
+                                          cost_shift, sweeps, labels_per_sweep, workspace, workspace_bytes, stream);
+    return launch_sweeps_ksets<float>(pvec, static_cast<const float*>(cost), nprop, labels, H, W, K, lamda, tpsi,
+                                      cost_shift, sweeps, labels_per_sweep, workspace, workspace_bytes, stream);
+  }
+  if (workspace_bytes < legacy_workspace_bytes(H, W, K)) return FLOWB200_EWORKSPACE;
   uint16_t* bp = static_cast<uint16_t*>(workspace);
   uint32_t* order;
   {

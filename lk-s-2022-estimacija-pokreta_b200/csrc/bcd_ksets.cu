@@ -1,0 +1,636 @@
+// BCD with compiled K-sets: the int32 programme of bcd.cu restructured around what the reference itself does --
+// it evaluates the K-sets S_l = {k : L1(v_l, u_k) < tpsi} ONCE per proposal set (pakovanje, daisy i flann.py:256-309,
+// the 2.6 GB packedksets cache) and only reads them inside bcd() (python bcd.py:131-142).  Here the cache is sparse:
+//
+//   kset_sort_kernel   per pixel: label indices ordered by the spatial-hash bucket of their flow vector
+//   kset_build_kernel  per (pixel, chain orientation): one RECORD = everything a chain step needs, contiguous:
+//                        16 B header | n x {vector, data cost | label, list offset | length} | uint16 entries
+//                      an entry = previous-pixel label k | L1(v_l, u_k) << 10, only pairs with L1 < tpsi.
+//                      Records are carved from an arena with one atomic cursor; a 64-bit descriptor per record
+//                      (offset | size) is the only index.  All (pixel, orientation) pairs are independent, so this
+//                      kernel is throughput bound, unlike the chains.
+//   kset_chain_kernel  one CTA per chain, one thread per label.  Thread 0 streams the chain's records into a ring
+//                      of shared-memory slots with bulk asynchronous copies (TMA engine, mbarrier completion) a few
+//                      steps ahead; a step is: wait for the slot, min over the label's entry list of
+//                      rep[k] + (L1 << ..), add the unary term, publish the new key, one block barrier.
+//
+// Keys are 32 bit: (dp - running minimum) << 9 | label, so that "smallest dp, lowest label on ties" (np.argmin,
+// python bcd.py:155/:175/:234) is one integer minimum and the block reduction is one REDUX + one shared atomic.
+// Subtracting the previous step's minimum from every dp changes no comparison.  Because of quirk Q1 (the truncation
+// candidate is ignored when S_l is not empty, :170-176) the spread of dp over the labels of a pixel is not bounded
+// by a constant; a chain whose relative dp leaves 22 bits re-runs itself with 64-bit keys (dp << 32 | label, no
+// renormalisation) -- same code, template parameter Wide.
+//
+// A record that does not fit (arena exhausted, larger than a slot, data cost out of 22 bits) gets descriptor 0 and
+// its step is evaluated densely from pvec/cost inside the chain kernel, so any workspace size gives the exact result.
+#include <type_traits>
+
+#include "bcd_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace flowb200 {
+
+namespace {
+
+constexpr uint32_t kRngEmpty = 0x0000FFFFu;   // first = 0xFFFF, last+1 = 0
+constexpr int kLabelBits = 9;                 // K <= 512
+constexpr uint32_t kLabelMask = (1u << kLabelBits) - 1;
+constexpr int kRecHeader = 16;
+constexpr int kMaxSlots = 4;
+constexpr uint32_t kCostLimit = 1u << 22;     // data cost field of a record entry (and overflow threshold of a narrow dp)
+
+__device__ __forceinline__ int cidx(int k) { return k + (k >> 5); }
+
+template <typename CostT>
+__device__ __forceinline__ int32_t quant_cost(CostT c, double lamda, int shift) {
+  if constexpr (std::is_integral<CostT>::value) return (int32_t)c;
+  else return (int32_t)rint(__dmul_rn(__dmul_rn(lamda, (double)c), (double)(1 << shift)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// sort: one warp per pixel, counting sort of the label indices by bucket key (order inside a bucket is arbitrary)
+// ------------------------------------------------------------------------------------------------
+constexpr int kSortWarps = 8;
+constexpr int kCntSize = kHashSize + kHashSize / 32;   // 1056, a multiple of 4
+
+__global__ void __launch_bounds__(kSortWarps * 32)
+kset_sort_kernel(const int32_t* __restrict__ pvec, const int32_t* __restrict__ nprop, int npix, int K, int Kst,
+                 int bshift, uint16_t* __restrict__ sorig) {
+  __shared__ __align__(16) int cnt_s[kSortWarps][kCntSize];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* cnt = cnt_s[warp];
+  for (int pix = blockIdx.x * kSortWarps + warp; pix < npix; pix += gridDim.x * kSortWarps) {
+    const int n = nprop[pix];
+    const int32_t* v = pvec + (size_t)pix * K;
+    uint16_t* o = sorig + (size_t)pix * Kst;
+    for (int i = lane; i < kCntSize / 4; i += 32) reinterpret_cast<int4*>(cnt)[i] = make_int4(0, 0, 0, 0);
+    __syncwarp();
+    for (int j = lane; j < n; j += 32) atomicAdd(&cnt[cidx(bucket_key(v[j], bshift))], 1);
+    __syncwarp();
+    // exclusive scan: lane owns counters [32*lane, 32*lane+32), stored at 33*lane + i (conflict free)
+    int sum = 0;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) sum += cnt[lane * 33 + i];
+    int pre = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, pre, off);
+      if (lane >= off) pre += t;
+    }
+    pre -= sum;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      const int c = cnt[lane * 33 + i];
+      cnt[lane * 33 + i] = pre;
+      pre += c;
+    }
+    __syncwarp();
+    for (int j = lane; j < n; j += 32) {
+      const int pos = atomicAdd(&cnt[cidx(bucket_key(v[j], bshift))], 1);
+      o[pos] = (uint16_t)j;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// build: one warp per record
+// ------------------------------------------------------------------------------------------------
+constexpr int kBuildWarps = 8;
+
+// previous pixel of `p` in the chain of orientation `orient` (0 = column chain, 1 = row chain) that visits it, or -1
+// at the start of the chain (python bcd.py:265-277: even columns run down, even rows right to left, odd columns up,
+// odd rows left to right)
+__device__ __forceinline__ int prev_pixel(int y, int x, int orient, int H, int W) {
+  if (orient == 0) {
+    const int yq = (x & 1) ? y + 1 : y - 1;
+    return (yq < 0 || yq >= H) ? -1 : yq * W + x;
+  }
+  const int xq = (y & 1) ? x - 1 : x + 1;
+  return (xq < 0 || xq >= W) ? -1 : y * W + xq;
+}
+
+// candidate ranges of vector v in the previous pixel's sorted label array: up to three [t0, t1) (one per bucket row)
+struct Ranges {
+  int t0[3], t1[3];
+};
+__device__ __forceinline__ Ranges lookup_ranges(const uint32_t* rng, int32_t v, int bshift) {
+  Ranges R;
+  const int by = vec_dy(v) >> bshift, bx = vec_dx(v) >> bshift;
+  const int kx0 = bkt_x(bx - 1), kx1 = bkt_x(bx), kx2 = bkt_x(bx + 1);
+  int last_row = -1;
+#pragma unroll
+  for (int oy = 0; oy < 3; ++oy) {
+    const int ky = bkt_y(by + oy - 1);
+    R.t0[oy] = R.t1[oy] = 0;
+    if (ky != last_row) {   // clamped rows can coincide: scan each bucket row once
+      const uint32_t* row = rng + (ky << 6);
+      const uint32_t r0 = row[kx0], r1 = row[kx1], r2 = row[kx2];
+      const int a = (int)min(min(r0 & 0xFFFFu, r1 & 0xFFFFu), r2 & 0xFFFFu);
+      const int b = (int)max(max(r0 >> 16, r1 >> 16), r2 >> 16);
+      if (b > a) {
+        R.t0[oy] = a;
+        R.t1[oy] = b;
+      }
+    }
+    last_row = ky;
+  }
+  return R;
+}
+
+template <typename CostT>
+__global__ void __launch_bounds__(kBuildWarps * 32)
+kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cost, const int32_t* __restrict__ nprop,
+                  const uint16_t* __restrict__ sorig, int H, int W, int K, int Kst, int Kpad, int tpsi, int bshift,
+                  int shift, double lamda, uint32_t slot_bytes, unsigned char* __restrict__ arena,
+                  unsigned long long arena_bytes, unsigned long long* __restrict__ cursor,
+                  unsigned long long* __restrict__ desc) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per warp: rng[kHashSize] u32 | vq[Kpad] i32 | cb[Kpad] u32 | kq[Kpad] u16 | ln[Kpad] u16
+  const size_t per_warp = (size_t)kHashSize * 4 + (size_t)Kpad * 12;
+  unsigned char* base = smem_raw + warp * per_warp;
+  uint32_t* rng = reinterpret_cast<uint32_t*>(base);
+  int32_t* vq = reinterpret_cast<int32_t*>(rng + kHashSize);
+  uint32_t* cb = reinterpret_cast<uint32_t*>(vq + Kpad);
+  uint16_t* kq = reinterpret_cast<uint16_t*>(cb + Kpad);
+  uint16_t* ln = kq + Kpad;
+  for (int i = lane; i < kHashSize; i += 32) rng[i] = kRngEmpty;
+  __syncwarp();
+
+  const int npix = H * W;
+  const int ntask = 2 * npix;
+  for (int task = blockIdx.x * kBuildWarps + warp; task < ntask; task += gridDim.x * kBuildWarps) {
+    const int orient = task >= npix ? 1 : 0;
+    const int p = task - orient * npix;
+    const int y = p / W, x = p - y * W;
+    const int q = prev_pixel(y, x, orient, H, W);
+    const int n = nprop[p];
+    const int nq = q >= 0 ? nprop[q] : 0;
+    const int32_t* vp = pvec + (size_t)p * K;
+    const CostT* cp = cost + (size_t)p * K;
+
+    // previous pixel's labels in bucket order; every bucket's [first, last+1) range
+    if (q >= 0) {
+      const int32_t* vqg = pvec + (size_t)q * K;
+      const uint16_t* sq = sorig + (size_t)q * Kst;
+      for (int s = lane; s < nq; s += 32) {
+        const int k = sq[s];
+        kq[s] = (uint16_t)k;
+        vq[s] = vqg[k];
+      }
+      __syncwarp();
+      for (int s = lane; s < nq; s += 32) {
+        const int key = bucket_key(vq[s], bshift);
+        uint16_t* half = reinterpret_cast<uint16_t*>(rng + key);
+        if (s == 0 || bucket_key(vq[s - 1], bshift) != key) half[0] = (uint16_t)s;
+        if (s == nq - 1 || bucket_key(vq[s + 1], bshift) != key) half[1] = (uint16_t)(s + 1);
+      }
+      __syncwarp();
+    }
+
+    // pass A: candidates per label -> list offsets (lists are allocated by candidate count: gaps, but one evaluation)
+    uint32_t total = 0;
+    bool cost_ok = true;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+      const int j = j0 + lane;
+      uint32_t c = 0;
+      if (j < n) {
+        if (q >= 0) {
+          const Ranges R = lookup_ranges(rng, vp[j], bshift);
+          c = (uint32_t)((R.t1[0] - R.t0[0]) + (R.t1[1] - R.t0[1]) + (R.t1[2] - R.t0[2]));
+        }
+        const int32_t m = quant_cost<CostT>(cp[j], lamda, shift);
+        cost_ok = cost_ok && m >= 0 && (uint32_t)m < kCostLimit;
+      }
+      uint32_t inc = c;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+      }
+      if (j < n) cb[j] = total + inc - c;
+      total += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    cost_ok = __all_sync(0xffffffffu, cost_ok);
+    const unsigned long long bytes = ((unsigned long long)kRecHeader + 12ull * n + 2ull * total + 15ull) & ~15ull;
+    bool ok = cost_ok && bytes <= slot_bytes && total < (1u << 22);
+    unsigned long long off = 0;
+    if (ok) {
+      if (lane == 0) off = atomicAdd(cursor, bytes);
+      off = __shfl_sync(0xffffffffu, off, 0);
+      ok = off + bytes <= arena_bytes;
+    }
+    if (ok) {
+      unsigned char* rec = arena + off;
+      uint32_t* st = reinterpret_cast<uint32_t*>(rec + kRecHeader);
+      uint16_t* ents = reinterpret_cast<uint16_t*>(rec + kRecHeader + 12 * (size_t)n);
+      // pass B: evaluate the candidates, emit the members
+      for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        if (j < n) {
+          const int32_t v = vp[j];
+          uint32_t m = 0;
+          const uint32_t cbase = cb[j];
+          if (q >= 0) {
+            const Ranges R = lookup_ranges(rng, v, bshift);
+            const int dy = vec_dy(v), dx = vec_dx(v);
+            uint16_t* e = ents + cbase;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+              for (int t = R.t0[r]; t < R.t1[r]; ++t) {
+                const int l1 = l1_vec(dy, dx, vq[t]);
+                if (l1 < tpsi) e[m++] = (uint16_t)(kq[t] | (l1 << 10));
+              }
+          }
+          st[3 * j + 0] = (uint32_t)v;
+          st[3 * j + 1] = ((uint32_t)quant_cost<CostT>(cp[j], lamda, shift) << 10) | (uint32_t)j;
+          st[3 * j + 2] = (cbase << 10) | m;
+        }
+      }
+      if (lane == 0) {
+        uint32_t* h = reinterpret_cast<uint32_t*>(rec);
+        h[0] = (uint32_t)n;
+        h[1] = total;
+        h[2] = 0;
+        h[3] = 0;
+      }
+    }
+    if (lane == 0) desc[task] = ok ? ((off >> 4) | ((bytes >> 4) << 40)) : 0ull;
+    // empty the touched buckets for the next record
+    __syncwarp();
+    for (int s = lane; s < nq; s += 32) rng[bucket_key(vq[s], bshift)] = kRngEmpty;
+    __syncwarp();
+  }
+  (void)ln;
+}
+
+// ------------------------------------------------------------------------------------------------
+// chains
+// ------------------------------------------------------------------------------------------------
+template <bool Wide> struct KeyOf { using type = uint32_t; };
+template <> struct KeyOf<true> { using type = unsigned long long; };
+
+template <bool Wide>
+__device__ __forceinline__ typename KeyOf<Wide>::type key_inf() {
+  if constexpr (Wide) return ~0ull;
+  else return 0xFFFFFFFFu;
+}
+// key of (dp, label); dp term d added to a key
+template <bool Wide>
+__device__ __forceinline__ typename KeyOf<Wide>::type make_key(uint32_t dp, uint32_t label) {
+  if constexpr (Wide) return ((unsigned long long)dp << 32) | label;
+  else return (dp << kLabelBits) | label;
+}
+template <bool Wide>
+__device__ __forceinline__ typename KeyOf<Wide>::type key_add(typename KeyOf<Wide>::type k, uint32_t d) {
+  if constexpr (Wide) return k + ((unsigned long long)d << 32);
+  else return k + (d << kLabelBits);
+}
+template <bool Wide>
+__device__ __forceinline__ uint32_t key_dp(typename KeyOf<Wide>::type k) {
+  if constexpr (Wide) return (uint32_t)(k >> 32);
+  else return k >> kLabelBits;
+}
+template <bool Wide>
+__device__ __forceinline__ uint32_t key_label(typename KeyOf<Wide>::type k) {
+  if constexpr (Wide) return (uint32_t)k;
+  else return k & kLabelMask;
+}
+__device__ __forceinline__ uint32_t warp_min_key(uint32_t k) { return __reduce_min_sync(0xffffffffu, k); }
+__device__ __forceinline__ unsigned long long warp_min_key(unsigned long long k) {
+  const uint32_t hi = (uint32_t)(k >> 32), lo = (uint32_t)k;
+  const uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
+  const uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+  return ((unsigned long long)mh << 32) | ml;
+}
+
+struct ChainArgs {
+  const int32_t* pvec;
+  const void* cost;
+  const int32_t* nprop;
+  int32_t* labels;
+  uint16_t* bp;
+  const unsigned long long* desc;
+  const unsigned char* arena;
+  int H, W, K, Kpad, phase, tpsi, shift, nslots;
+  uint32_t slot_bytes;
+  double lamda;
+};
+
+// Returns true (uniformly) when a narrow run overflowed and nothing was written.
+template <bool Wide, typename CostT, int T>
+__device__ __forceinline__ bool chain_body(const ChainArgs& a, unsigned char* smem_raw) {
+  using Key = typename KeyOf<Wide>::type;
+  const Key INF = key_inf<Wide>();
+  const ChainGeom g = chain_geom(a.phase, blockIdx.x, a.H, a.W);
+  const int t = threadIdx.x, lane = t & 31;
+  const int K = a.K, Kpad = a.Kpad, S = a.nslots, shift = a.shift, tpsi = a.tpsi;
+  const int orient = a.phase & 1;
+  const unsigned long long* dsc = a.desc + (size_t)orient * a.H * a.W;
+  const CostT* cost = static_cast<const CostT*>(a.cost);
+
+  // shared memory: mbar[4] | present[4] | trunc[3] (+pad) | rep[2][Kpad] | oldvec[len] | vprev[Kpad] | slots
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* present_s = reinterpret_cast<uint32_t*>(smem_raw + 32);
+  Key* trunc_s = reinterpret_cast<Key*>(smem_raw + 48);                       // 3 keys (<= 24 bytes) + pad -> 80
+  Key* rep_s = reinterpret_cast<Key*>(smem_raw + 80);
+  int32_t* oldvec = reinterpret_cast<int32_t*>(smem_raw + 80 + 2 * (size_t)Kpad * 8);   // sized for wide keys
+  int32_t* vprev = oldvec + g.len;
+  const size_t slots_off = (80 + 2 * (size_t)Kpad * 8 + 4 * (size_t)g.len + 4 * (size_t)Kpad + 127) & ~(size_t)127;
+  unsigned char* slots = smem_raw + slots_off;
+
+  auto pixel = [&](int i) { return (g.sy + i * g.ystep) * a.W + (g.sx + i * g.xstep); };
+
+  for (int i = t; i < g.len; i += T) {
+    const int p = pixel(i);
+    oldvec[i] = a.pvec[(size_t)p * K + a.labels[p]];
+  }
+  if (t < 3) trunc_s[t] = INF;
+  if (t == 0) {
+    for (int s = 0; s < S; ++s) ptx::mbar_init(&mbar[s], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+
+  // producer (thread 0): record i goes to slot i % S; absent records complete their barrier phase without bytes
+  unsigned long long d_next = 0;
+  auto issue = [&](int i, unsigned long long d) {
+    const int slot = i % S;
+    const uint32_t bytes = (uint32_t)(d >> 40) << 4;
+    present_s[slot] = bytes;
+    if (bytes) {
+      ptx::mbar_arrive_expect_tx(&mbar[slot], bytes);
+      ptx::bulk_load(slots + (size_t)slot * a.slot_bytes, a.arena + ((d & ((1ull << 40) - 1)) << 4), bytes, &mbar[slot]);
+    } else {
+      ptx::mbar_arrive(&mbar[slot]);
+    }
+  };
+  if (t == 0) {
+    for (int i = 0; i < S && i < g.len; ++i) issue(i, dsc[pixel(i)]);
+    if (S < g.len) d_next = dsc[pixel(S)];
+  }
+
+  uint16_t* bp_chain = a.bp + (size_t)blockIdx.x * g.len * Kpad;
+  const uint32_t tpsi_dp = (uint32_t)tpsi << shift;
+  uint32_t ovf = 0;
+
+  for (int i = 0; i < g.len; ++i) {
+    const int slot = i % S;
+    ptx::mbar_wait(&mbar[slot], (uint32_t)(i / S) & 1u);
+    const uint32_t present = present_s[slot];
+    const Key* rp = rep_s + ((i & 1) ^ 1) * Kpad;
+    Key* rc = rep_s + (i & 1) * Kpad;
+    const Key trunc_prev = trunc_s[(i + 2) % 3];
+    // unary side terms (sidepsi :84-88): the chain's own neighbours with their labels from before this call
+    const int32_t ov_a = i + 1 < g.len ? oldvec[i + 1] : 0, ov_b = i > 0 ? oldvec[i - 1] : 0;
+    Key key = INF;
+    if (present) {
+      const unsigned char* rec = slots + (size_t)slot * a.slot_bytes;
+      const int n = (int)*reinterpret_cast<const uint32_t*>(rec);
+      if (t < n) {
+        const uint32_t* st = reinterpret_cast<const uint32_t*>(rec + kRecHeader) + 3 * t;
+        const int32_t v = (int32_t)st[0];
+        const uint32_t co = st[1], ol = st[2];
+        const uint32_t orig = co & 1023u;
+        const int dy = vec_dy(v), dx = vec_dx(v);
+        uint32_t psi = 0;
+        if (i + 1 < g.len) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, ov_a));
+        if (i > 0) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, ov_b));
+        const uint32_t U = (co >> 10) + (psi << shift);
+        uint32_t dp = U;
+        if (i > 0) {
+          const int len = (int)(ol & 1023u);
+          const uint16_t* e = reinterpret_cast<const uint16_t*>(rec + kRecHeader + 12 * (size_t)n) + (ol >> 10);
+          Key acc = len ? INF : trunc_prev;   // quirk Q1: the truncation candidate only when the K-set is empty
+          Key acc1 = INF, acc2 = INF, acc3 = INF;
+          const int last = len - 1;
+          for (int x = 0; x < len; x += 4) {
+            const uint32_t e0 = e[x], e1 = e[min(x + 1, last)], e2 = e[min(x + 2, last)], e3 = e[min(x + 3, last)];
+            const Key c0 = key_add<Wide>(rp[e0 & 1023u], (e0 >> 10) << shift);
+            const Key c1 = key_add<Wide>(rp[e1 & 1023u], (e1 >> 10) << shift);
+            const Key c2 = key_add<Wide>(rp[e2 & 1023u], (e2 >> 10) << shift);
+            const Key c3 = key_add<Wide>(rp[e3 & 1023u], (e3 >> 10) << shift);
+            acc = min(acc, c0);
+            acc1 = min(acc1, c1);
+            acc2 = min(acc2, c2);
+            acc3 = min(acc3, c3);
+          }
+          acc = min(min(acc, acc1), min(acc2, acc3));
+          if constexpr (Wide) dp = key_dp<Wide>(acc) + U;
+          else dp = key_dp<Wide>(acc) - (key_dp<Wide>(trunc_prev) - tpsi_dp) + U;
+          bp_chain[(size_t)i * Kpad + orig] = (uint16_t)key_label<Wide>(acc);
+        }
+        if constexpr (!Wide) ovf |= dp >> 22;
+        key = make_key<Wide>(dp, orig);
+        rc[orig] = key;
+      }
+    } else {
+      // dense step: the record was not stored; evaluate the K-set from the proposal arrays
+      const int p = pixel(i);
+      const int n = a.nprop[p];
+      int nq = 0;
+      if (i > 0) {
+        const int q = pixel(i - 1);
+        nq = a.nprop[q];
+        for (int k = t; k < nq; k += T) vprev[k] = a.pvec[(size_t)q * K + k];
+      }
+      __syncthreads();
+      if (t < n) {
+        const int32_t v = a.pvec[(size_t)p * K + t];
+        const int dy = vec_dy(v), dx = vec_dx(v);
+        uint32_t psi = 0;
+        if (i + 1 < g.len) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, ov_a));
+        if (i > 0) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, ov_b));
+        const uint32_t U = (uint32_t)quant_cost<CostT>(cost[(size_t)p * K + t], a.lamda, shift) + (psi << shift);
+        uint32_t dp = U;
+        if (i > 0) {
+          Key acc = INF;
+          for (int k = 0; k < nq; ++k) {
+            const int l1 = l1_vec(dy, dx, vprev[k]);
+            if (l1 < tpsi) acc = min(acc, key_add<Wide>(rp[k], (uint32_t)l1 << shift));
+          }
+          if (acc == INF) acc = trunc_prev;
+          if constexpr (Wide) dp = key_dp<Wide>(acc) + U;
+          else dp = key_dp<Wide>(acc) - (key_dp<Wide>(trunc_prev) - tpsi_dp) + U;
+          bp_chain[(size_t)i * Kpad + t] = (uint16_t)key_label<Wide>(acc);
+        }
+        if constexpr (!Wide) ovf |= dp >> 22;
+        key = make_key<Wide>(dp, (uint32_t)t);
+        rc[t] = key;
+      }
+    }
+    // block minimum of (dp + tpsi, label) for the next step's truncation candidate (:152-157), lowest label on ties
+    const Key wmin = warp_min_key(key);
+    if (lane == 0 && wmin != INF) atomicMin(&trunc_s[i % 3], key_add<Wide>(wmin, tpsi_dp));
+    if (t == 0) trunc_s[(i + 1) % 3] = INF;
+    __syncthreads();
+    if (t == 0 && i + S < g.len) {
+      issue(i + S, d_next);
+      if (i + S + 1 < g.len) d_next = dsc[pixel(i + S + 1)];
+    }
+  }
+
+  if constexpr (!Wide) {
+    if (__syncthreads_or((int)ovf)) {
+      // leave the barriers reusable for the wide re-run
+      if (t == 0)
+        for (int s = 0; s < S; ++s)
+          asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(ptx::smem_u32(&mbar[s])) : "memory");
+      __syncthreads();
+      return true;
+    }
+  }
+
+  // final label: lowest-index argmin of dp_last (:231-237) = label field of the last block minimum; backtrack
+  // (:238-253) through the back-pointers, staged through shared memory a segment of rows at a time
+  int lab = (int)key_label<Wide>(trunc_s[(g.len - 1) % 3]);
+  const int rows_cap = max(1, (int)(((size_t)S * a.slot_bytes) / ((size_t)Kpad * 2)));
+  uint16_t* seg = reinterpret_cast<uint16_t*>(slots);
+  const int vec_per_row = Kpad / 8;   // uint4 = 8 back-pointers
+  for (int hi = g.len - 1; hi >= 1; hi -= rows_cap) {
+    const int lo = max(1, hi - rows_cap + 1);
+    const int nrow = hi - lo + 1;
+    const uint4* src = reinterpret_cast<const uint4*>(bp_chain + (size_t)lo * Kpad);
+    uint4* dst = reinterpret_cast<uint4*>(seg);
+    for (int x = t; x < nrow * vec_per_row; x += T) dst[x] = src[x];
+    __syncthreads();
+    if (t == 0) {
+      for (int i = hi; i >= lo; --i) {
+        a.labels[pixel(i)] = lab;
+        lab = seg[(size_t)(i - lo) * Kpad + lab];
+      }
+    }
+    __syncthreads();   // (uniform: lab is only meaningful in thread 0)
+  }
+  if (t == 0) a.labels[pixel(0)] = lab;
+  return false;
+}
+
+template <typename CostT, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) kset_chain_kernel(const ChainArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (!chain_body<false, CostT, T>(a, smem_raw)) return;
+  chain_body<true, CostT, T>(a, smem_raw);
+}
+
+struct KsetLayout {
+  size_t bp, sorig, desc, cursor, arena, arena_bytes, total;
+  int Kst, Kpad;
+};
+
+KsetLayout kset_layout(int H, int W, int K, size_t workspace_bytes) {
+  KsetLayout L{};
+  L.Kpad = (K + 31) / 32 * 32;
+  L.Kst = (K + 7) / 8 * 8;
+  const size_t n = (size_t)H * W;
+  const size_t col = (size_t)((W + 1) / 2) * H, row = (size_t)((H + 1) / 2) * W;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes);
+    return o;
+  };
+  L.bp = take((col > row ? col : row) * L.Kpad * sizeof(uint16_t));
+  L.sorig = take(n * L.Kst * sizeof(uint16_t));
+  L.desc = take(2 * n * sizeof(unsigned long long));
+  L.cursor = take(256);
+  L.arena = off;
+  if (workspace_bytes == 0) {
+    // default budget: header + 12 B per label + room for ~10 candidate entries per label, per record
+    L.arena_bytes = 2 * n * (size_t)(kRecHeader + 12 * K + 20 * K);
+  } else {
+    L.arena_bytes = workspace_bytes > off ? (workspace_bytes - off) & ~(size_t)15 : 0;
+  }
+  L.total = off + align_up(L.arena_bytes);
+  return L;
+}
+
+}  // namespace
+
+size_t ksets_workspace_bytes(int H, int W, int K) { return kset_layout(H, W, K, 0).total; }
+
+template <typename CostT>
+int launch_sweeps_ksets(const int32_t* pvec, const CostT* cost, const int32_t* nprop, int32_t* labels, int H, int W,
+                        int K, double lamda, int tpsi, int shift, int sweeps, int32_t* labels_per_sweep,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (K > 512 || tpsi < 1 || tpsi > 8) return FLOWB200_EUNSUPPORTED;
+  const KsetLayout L = kset_layout(H, W, K, workspace_bytes);
+  if (workspace_bytes < L.arena) return FLOWB200_EWORKSPACE;
+  char* ws = static_cast<char*>(workspace);
+  const int Kpad = L.Kpad;
+  const int npix = H * W;
+  int bshift = 0;
+  while ((1 << bshift) < tpsi) ++bshift;
+
+  void (*kern)(const ChainArgs) = nullptr;
+  int T = 0, minb = 1;
+#define FB_KS_CASE(TT, MB) if (!kern && K <= TT) { kern = kset_chain_kernel<CostT, TT, MB>; T = TT; minb = MB; }
+  FB_KS_CASE(64, 8) FB_KS_CASE(128, 6) FB_KS_CASE(192, 5) FB_KS_CASE(256, 4) FB_KS_CASE(320, 4)
+  FB_KS_CASE(384, 3) FB_KS_CASE(512, 2)
+#undef FB_KS_CASE
+  if (!kern) return FLOWB200_EUNSUPPORTED;
+
+  // ring of record slots: as many (<= 4) as keep `minb` chains per SM resident
+  const int maxlen = H > W ? H : W;
+  const size_t fixed = ((80 + 2 * (size_t)Kpad * 8 + 4 * (size_t)maxlen + 4 * (size_t)Kpad + 127) & ~(size_t)127);
+  uint32_t slot_bytes = (uint32_t)((kRecHeader + 12 * (size_t)Kpad + 24 * (size_t)Kpad + 127) & ~(size_t)127);
+  int nslots = kMaxSlots;
+  const size_t budget = (size_t)(227 * 1024) / minb - 1024;
+  while (nslots > 2 && fixed + (size_t)nslots * slot_bytes > budget) --nslots;
+  if (fixed + (size_t)nslots * slot_bytes > budget) {
+    // long chains (large images): fewer resident chains rather than smaller slots
+    if (fixed + 2 * (size_t)slot_bytes > (size_t)227 * 1024) return FLOWB200_EUNSUPPORTED;
+  }
+  const size_t smem = fixed + (size_t)nslots * slot_bytes;
+  FB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+  if (sweeps > 0) {
+    uint16_t* sorig = reinterpret_cast<uint16_t*>(ws + L.sorig);
+    unsigned long long* cursor = reinterpret_cast<unsigned long long*>(ws + L.cursor);
+    FB_CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), stream));
+    kset_sort_kernel<<<min((npix + kSortWarps - 1) / kSortWarps, 8 * kNumSMs), kSortWarps * 32, 0, stream>>>(
+        pvec, nprop, npix, K, L.Kst, bshift, sorig);
+    FB_LAUNCH_CHECK();
+    const size_t bsmem = (size_t)kBuildWarps * ((size_t)kHashSize * 4 + (size_t)Kpad * 12);
+    auto bk = kset_build_kernel<CostT>;
+    FB_CUDA_CHECK(cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+    const int bctas = (int)(227 * 1024 / (bsmem + 1024));
+    bk<<<min((2 * npix + kBuildWarps - 1) / kBuildWarps, max(1, bctas) * kNumSMs), kBuildWarps * 32, bsmem, stream>>>(
+        pvec, cost, nprop, sorig, H, W, K, L.Kst, Kpad, tpsi, bshift, shift, lamda, slot_bytes,
+        reinterpret_cast<unsigned char*>(ws + L.arena), (unsigned long long)L.arena_bytes, cursor,
+        reinterpret_cast<unsigned long long*>(ws + L.desc));
+    FB_LAUNCH_CHECK();
+  }
+  ChainArgs a{};
+  a.pvec = pvec;
+  a.cost = cost;
+  a.nprop = nprop;
+  a.labels = labels;
+  a.bp = reinterpret_cast<uint16_t*>(ws + L.bp);
+  a.desc = reinterpret_cast<const unsigned long long*>(ws + L.desc);
+  a.arena = reinterpret_cast<const unsigned char*>(ws + L.arena);
+  a.H = H; a.W = W; a.K = K; a.Kpad = Kpad; a.tpsi = tpsi; a.shift = shift; a.nslots = nslots;
+  a.slot_bytes = slot_bytes;
+  a.lamda = lamda;
+  for (int w = 0; w < sweeps; ++w) {
+    for (int phase = 0; phase < 4; ++phase) {
+      const int nch = phase_chains(phase, H, W);
+      if (nch == 0) continue;
+      a.phase = phase;
+      kern<<<nch, T, smem, stream>>>(a);
+      FB_LAUNCH_CHECK();
+    }
+    if (labels_per_sweep)
+      FB_CUDA_CHECK(cudaMemcpyAsync(labels_per_sweep + (size_t)w * H * W, labels, sizeof(int32_t) * H * W,
+                                    cudaMemcpyDeviceToDevice, stream));
+  }
+  return FLOWB200_OK;
+}
+
+template int launch_sweeps_ksets<int32_t>(const int32_t*, const int32_t*, const int32_t*, int32_t*, int, int, int, double,
+                                          int, int, int, int32_t*, void*, size_t, cudaStream_t);
+template int launch_sweeps_ksets<float>(const int32_t*, const float*, const int32_t*, int32_t*, int, int, int, double, int,
+                                        int, int, int32_t*, void*, size_t, cudaStream_t);
+
+}  // namespace flowb200
