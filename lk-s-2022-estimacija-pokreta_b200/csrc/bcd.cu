@@ -602,9 +602,9 @@ static size_t legacy_workspace_bytes(int H, int W, int K) {
 
 // The int32 programme runs on compiled K-sets (bcd_ksets.cu) unless FLOWB200_BCD_LEGACY is set in the environment
 // (or tpsi > 8); the float64 modes always run the implementation in this file.
-static bool use_ksets(int tpsi) {
+static bool use_ksets(int tpsi, int cost_shift) {
   static const bool legacy = getenv("FLOWB200_BCD_LEGACY") != nullptr;
-  return !legacy && tpsi >= 1 && tpsi <= 8;
+  return !legacy && tpsi >= 1 && tpsi <= 8 && cost_shift >= 3;
 }
 
 extern "C" size_t flowb200_bcd_workspace_bytes(int H, int W, int K) {
@@ -621,7 +621,7 @@ extern "C" int flowb200_bcd(const int32_t* pvec, const void* cost, const int32_t
   if (H <= 0 || W <= 0 || K <= 0 || K > 512 || sweeps < 0 || tpsi < 0) return FLOWB200_EINVAL;
   if (H > 16384 || W > 16384) return FLOWB200_EINVAL;
   const bool int_mode = bcd_mode == FLOWB200_BCD_INT32 || bcd_mode == FLOWB200_BCD_INT32_F32COST;
-  if (int_mode && use_ksets(tpsi)) {
+  if (int_mode && use_ksets(tpsi, cost_shift)) {
     // any workspace that holds the fixed part is accepted: records that do not fit are evaluated densely
     if (cost_shift < 0 || cost_shift > 14) return FLOWB200_EINVAL;
     if (bcd_mode == FLOWB200_BCD_INT32)

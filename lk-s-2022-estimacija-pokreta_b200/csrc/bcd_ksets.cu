@@ -23,6 +23,7 @@
 //
 // A record that does not fit (arena exhausted, larger than a slot, data cost out of 22 bits) gets descriptor 0 and
 // its step is evaluated densely from pvec/cost inside the chain kernel, so any workspace size gives the exact result.
+#include <algorithm>
 #include <type_traits>
 
 #include "bcd_common.cuh"
@@ -36,8 +37,10 @@ constexpr uint32_t kRngEmpty = 0x0000FFFFu;   // first = 0xFFFF, last+1 = 0
 constexpr int kLabelBits = 9;                 // K <= 512
 constexpr uint32_t kLabelMask = (1u << kLabelBits) - 1;
 constexpr int kRecHeader = 16;
-constexpr int kMaxSlots = 4;
-constexpr uint32_t kCostLimit = 1u << 22;     // data cost field of a record entry (and overflow threshold of a narrow dp)
+// Try 32-bit keys first and re-run a chain with 64-bit keys when its relative dp overflows.  Measured on the bench
+// workload: ~5 % of the row chains overflow (label clusters that stay 16 units per step worse than the best label,
+// which quirk Q1 keeps alive), and a phase lasts as long as its slowest chain, so the re-runs doubled the phase time.
+constexpr bool kNarrowFirst = false;
 
 __device__ __forceinline__ int cidx(int k) { return k + (k >> 5); }
 
@@ -55,7 +58,7 @@ constexpr int kCntSize = kHashSize + kHashSize / 32;   // 1056, a multiple of 4
 
 __global__ void __launch_bounds__(kSortWarps * 32)
 kset_sort_kernel(const int32_t* __restrict__ pvec, const int32_t* __restrict__ nprop, int npix, int K, int Kst,
-                 int bshift, uint16_t* __restrict__ sorig) {
+                 int bshift, uint16_t* __restrict__ sorig, int32_t* __restrict__ svec) {
   __shared__ __align__(16) int cnt_s[kSortWarps][kCntSize];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* cnt = cnt_s[warp];
@@ -63,6 +66,7 @@ kset_sort_kernel(const int32_t* __restrict__ pvec, const int32_t* __restrict__ n
     const int n = nprop[pix];
     const int32_t* v = pvec + (size_t)pix * K;
     uint16_t* o = sorig + (size_t)pix * Kst;
+    int32_t* ov = svec + (size_t)pix * Kst;
     for (int i = lane; i < kCntSize / 4; i += 32) reinterpret_cast<int4*>(cnt)[i] = make_int4(0, 0, 0, 0);
     __syncwarp();
     for (int j = lane; j < n; j += 32) atomicAdd(&cnt[cidx(bucket_key(v[j], bshift))], 1);
@@ -86,8 +90,10 @@ kset_sort_kernel(const int32_t* __restrict__ pvec, const int32_t* __restrict__ n
     }
     __syncwarp();
     for (int j = lane; j < n; j += 32) {
-      const int pos = atomicAdd(&cnt[cidx(bucket_key(v[j], bshift))], 1);
+      const int32_t vj = v[j];
+      const int pos = atomicAdd(&cnt[cidx(bucket_key(vj, bshift))], 1);
       o[pos] = (uint16_t)j;
+      ov[pos] = vj;
     }
     __syncwarp();
   }
@@ -95,8 +101,20 @@ kset_sort_kernel(const int32_t* __restrict__ pvec, const int32_t* __restrict__ n
 
 // ------------------------------------------------------------------------------------------------
 // build: one warp per record
+//
+// Record layout (16-byte aligned, at most one chain-kernel slot):
+//   [0,16)   uint32 n, nr (rounds = longest list), struct byte offset, entry byte offset
+//   [16,..)  uint16 roff[nr+1]: first entry of round r; round r holds entry r of every label whose list is longer
+//            than r.  Labels are stored in order of DECREASING list length, so these labels are positions
+//            0 .. cnt_r-1 and entry r of position t sits at roff[r] + t (jagged-diagonal storage): the chain
+//            kernel's lanes read consecutive uint16 and the lanes of a warp have (almost) equal trip counts.
+//   structs  n x {int32 vector; uint32 data cost (16) | original label (9) << 16 | list length (7) << 25}
+//   entries  uint16 (k << 3) | (L1 << 12): previous-pixel label k (original index) and L1(v_l, u_k) < tpsi
+//   (roff is stored in BYTES, i.e. doubled, so that the chain kernel adds it to a byte pointer)
 // ------------------------------------------------------------------------------------------------
-constexpr int kBuildWarps = 8;
+constexpr int kMaxList = 127;                  // list length field: 7 bits
+constexpr uint32_t kCostLimit16 = 1u << 16;    // data cost field: 16 bits
+constexpr int kStagePerLabel = 10;             // staging capacity: candidates per label of Kpad
 
 // previous pixel of `p` in the chain of orientation `orient` (0 = column chain, 1 = row chain) that visits it, or -1
 // at the start of the chain (python bcd.py:265-277: even columns run down, even rows right to left, odd columns up,
@@ -138,29 +156,47 @@ __device__ __forceinline__ Ranges lookup_ranges(const uint32_t* rng, int32_t v, 
   return R;
 }
 
+// Shared memory of one build CTA (one record at a time):
+// rng u32[kHashSize] | hist u32[128] | start u32[128] | misc u32[16] | vq2 int2[Kpad] | roff u16[136] |
+// kq3, ln, so, rk, inv, cq u16[Kpad] | stage u16[kStagePerLabel * Kpad]
+__host__ __device__ inline size_t build_smem_bytes(int Kpad) {
+  return (size_t)kHashSize * 4 + 128 * 4 * 2 + 64 + (size_t)Kpad * 8 + 136 * 2 + (size_t)Kpad * 2 * 6 +
+         (size_t)kStagePerLabel * Kpad * 2;
+}
+
+constexpr int kBuildThreads = 128;
+
 template <typename CostT>
-__global__ void __launch_bounds__(kBuildWarps * 32)
+__global__ void __launch_bounds__(kBuildThreads)
 kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ cost, const int32_t* __restrict__ nprop,
-                  const uint16_t* __restrict__ sorig, int H, int W, int K, int Kst, int Kpad, int tpsi, int bshift,
-                  int shift, double lamda, uint32_t slot_bytes, unsigned char* __restrict__ arena,
-                  unsigned long long arena_bytes, unsigned long long* __restrict__ cursor,
-                  unsigned long long* __restrict__ desc) {
+                  const uint16_t* __restrict__ sorig, const int32_t* __restrict__ svec, int H, int W, int K, int Kst,
+                  int Kpad, int tpsi, int bshift, int shift, double lamda, uint32_t slot_bytes,
+                  unsigned char* __restrict__ arena, unsigned long long arena_bytes,
+                  unsigned long long* __restrict__ cursor, unsigned long long* __restrict__ desc) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // per warp: rng[kHashSize] u32 | vq[Kpad] i32 | cb[Kpad] u32 | kq[Kpad] u16 | ln[Kpad] u16
-  const size_t per_warp = (size_t)kHashSize * 4 + (size_t)Kpad * 12;
-  unsigned char* base = smem_raw + warp * per_warp;
-  uint32_t* rng = reinterpret_cast<uint32_t*>(base);
-  int32_t* vq = reinterpret_cast<int32_t*>(rng + kHashSize);
-  uint32_t* cb = reinterpret_cast<uint32_t*>(vq + Kpad);
-  uint16_t* kq = reinterpret_cast<uint16_t*>(cb + Kpad);
-  uint16_t* ln = kq + Kpad;
-  for (int i = lane; i < kHashSize; i += 32) rng[i] = kRngEmpty;
-  __syncwarp();
+  const int t = threadIdx.x, lane = t & 31;
+  uint32_t* rng = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* hist = rng + kHashSize;
+  uint32_t* start = hist + 128;
+  uint32_t* misc = start + 128;          // [0] staged entries, [1] failure flag, [2] nr, [3] ok, [4..5] arena offset,
+                                         // [6] struct offset, [7] entry offset
+  int2* vq2 = reinterpret_cast<int2*>(misc + 16);
+  uint16_t* roff = reinterpret_cast<uint16_t*>(vq2 + Kpad);
+  uint16_t* kq3 = roff + 136;
+  uint16_t* ln = kq3 + Kpad;
+  uint16_t* so = ln + Kpad;
+  uint16_t* rk = so + Kpad;
+  uint16_t* inv = rk + Kpad;
+  uint16_t* cq = inv + Kpad;
+  uint16_t* stage = cq + Kpad;
+  const uint32_t stage_cap = (uint32_t)kStagePerLabel * Kpad;
+  for (int i = t; i < kHashSize; i += kBuildThreads) rng[i] = kRngEmpty;
+  if (t < 16) misc[t] = 0;
+  __syncthreads();
 
   const int npix = H * W;
   const int ntask = 2 * npix;
-  for (int task = blockIdx.x * kBuildWarps + warp; task < ntask; task += gridDim.x * kBuildWarps) {
+  for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
     const int orient = task >= npix ? 1 : 0;
     const int p = task - orient * npix;
     const int y = p / W, x = p - y * W;
@@ -169,100 +205,188 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
     const int nq = q >= 0 ? nprop[q] : 0;
     const int32_t* vp = pvec + (size_t)p * K;
     const CostT* cp = cost + (size_t)p * K;
+    const uint16_t* sp = sorig + (size_t)p * Kst;
+    const int32_t* svp = svec + (size_t)p * Kst;
 
-    // previous pixel's labels in bucket order; every bucket's [first, last+1) range
+    // 1. previous pixel's labels in bucket order
     if (q >= 0) {
-      const int32_t* vqg = pvec + (size_t)q * K;
       const uint16_t* sq = sorig + (size_t)q * Kst;
-      for (int s = lane; s < nq; s += 32) {
-        const int k = sq[s];
-        kq[s] = (uint16_t)k;
-        vq[s] = vqg[k];
+      const int32_t* svq = svec + (size_t)q * Kst;
+      for (int s = t; s < nq; s += kBuildThreads) {
+        const int32_t v = svq[s];
+        vq2[s] = make_int2(vec_dy(v), vec_dx(v));
+        kq3[s] = (uint16_t)((uint32_t)sq[s] << 3);
       }
-      __syncwarp();
-      for (int s = lane; s < nq; s += 32) {
-        const int key = bucket_key(vq[s], bshift);
-        uint16_t* half = reinterpret_cast<uint16_t*>(rng + key);
-        if (s == 0 || bucket_key(vq[s - 1], bshift) != key) half[0] = (uint16_t)s;
-        if (s == nq - 1 || bucket_key(vq[s + 1], bshift) != key) half[1] = (uint16_t)(s + 1);
-      }
-      __syncwarp();
     }
+    if (t < 128) hist[t] = 0;
+    __syncthreads();
+    // 2. every bucket's [first, last+1) range
+    for (int s = t; s < nq; s += kBuildThreads) {
+      const int2 u = vq2[s];
+      const int key = (bkt_y(u.x >> bshift) << 6) | bkt_x(u.y >> bshift);
+      uint16_t* half = reinterpret_cast<uint16_t*>(rng + key);
+      bool first = s == 0, last = s == nq - 1;
+      if (!first) {
+        const int2 a = vq2[s - 1];
+        first = ((bkt_y(a.x >> bshift) << 6) | bkt_x(a.y >> bshift)) != key;
+      }
+      if (!last) {
+        const int2 b = vq2[s + 1];
+        last = ((bkt_y(b.x >> bshift) << 6) | bkt_x(b.y >> bshift)) != key;
+      }
+      if (first) half[0] = (uint16_t)s;
+      if (last) half[1] = (uint16_t)(s + 1);
+    }
+    __syncthreads();
 
-    // pass A: candidates per label -> list offsets (lists are allocated by candidate count: gaps, but one evaluation)
-    uint32_t total = 0;
-    bool cost_ok = true;
-    for (int j0 = 0; j0 < n; j0 += 32) {
-      const int j = j0 + lane;
-      uint32_t c = 0;
-      if (j < n) {
-        if (q >= 0) {
-          const Ranges R = lookup_ranges(rng, vp[j], bshift);
-          c = (uint32_t)((R.t1[0] - R.t0[0]) + (R.t1[1] - R.t0[1]) + (R.t1[2] - R.t0[2]));
-        }
+    // 3. evaluate: this pixel's labels in bucket order too (neighbouring lanes scan the same or adjacent ranges, so
+    // their trip counts are similar); members are staged in shared memory, lists allocated by candidate count
+    for (int s0 = 0; s0 < n; s0 += kBuildThreads) {
+      const int s = s0 + t;
+      const bool act = s < n;
+      const int j = act ? (int)sp[s] : 0;
+      int dy = 0, dx = 0;
+      uint32_t c = 0, c0 = 0, c01 = 0;
+      int o0 = 0, o1 = 0, o2 = 0;
+      if (act) {
+        const int32_t v = svp[s];
+        dy = vec_dy(v);
+        dx = vec_dx(v);
         const int32_t m = quant_cost<CostT>(cp[j], lamda, shift);
-        cost_ok = cost_ok && m >= 0 && (uint32_t)m < kCostLimit;
+        if (m < 0 || (uint32_t)m >= kCostLimit16) misc[1] = 1;
+        cq[j] = (uint16_t)m;
+        if (q >= 0) {
+          const Ranges R = lookup_ranges(rng, v, bshift);
+          c0 = (uint32_t)(R.t1[0] - R.t0[0]);
+          c01 = c0 + (uint32_t)(R.t1[1] - R.t0[1]);
+          c = c01 + (uint32_t)(R.t1[2] - R.t0[2]);
+          o0 = R.t0[0];
+          o1 = R.t0[1] - (int)c0;
+          o2 = R.t0[2] - (int)c01;
+        }
       }
       uint32_t inc = c;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
-        if (lane >= off) inc += t;
+        uint32_t u = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += u;
       }
-      if (j < n) cb[j] = total + inc - c;
-      total += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    cost_ok = __all_sync(0xffffffffu, cost_ok);
-    const unsigned long long bytes = ((unsigned long long)kRecHeader + 12ull * n + 2ull * total + 15ull) & ~15ull;
-    bool ok = cost_ok && bytes <= slot_bytes && total < (1u << 22);
-    unsigned long long off = 0;
-    if (ok) {
-      if (lane == 0) off = atomicAdd(cursor, bytes);
-      off = __shfl_sync(0xffffffffu, off, 0);
-      ok = off + bytes <= arena_bytes;
-    }
-    if (ok) {
-      unsigned char* rec = arena + off;
-      uint32_t* st = reinterpret_cast<uint32_t*>(rec + kRecHeader);
-      uint16_t* ents = reinterpret_cast<uint16_t*>(rec + kRecHeader + 12 * (size_t)n);
-      // pass B: evaluate the candidates, emit the members
-      for (int j0 = 0; j0 < n; j0 += 32) {
-        const int j = j0 + lane;
-        if (j < n) {
-          const int32_t v = vp[j];
-          uint32_t m = 0;
-          const uint32_t cbase = cb[j];
-          if (q >= 0) {
-            const Ranges R = lookup_ranges(rng, v, bshift);
-            const int dy = vec_dy(v), dx = vec_dx(v);
-            uint16_t* e = ents + cbase;
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-              for (int t = R.t0[r]; t < R.t1[r]; ++t) {
-                const int l1 = l1_vec(dy, dx, vq[t]);
-                if (l1 < tpsi) e[m++] = (uint16_t)(kq[t] | (l1 << 10));
-              }
-          }
-          st[3 * j + 0] = (uint32_t)v;
-          st[3 * j + 1] = ((uint32_t)quant_cost<CostT>(cp[j], lamda, shift) << 10) | (uint32_t)j;
-          st[3 * j + 2] = (cbase << 10) | m;
+      const uint32_t warp_total = __shfl_sync(0xffffffffu, inc, 31);
+      uint32_t wbase = 0;
+      if (lane == 0) wbase = atomicAdd(&misc[0], warp_total);
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (wbase + warp_total > stage_cap) {   // warp-uniform
+        if (lane == 0) misc[1] = 1;
+      } else if (act) {
+        const uint32_t sbase = wbase + inc - c;
+        uint16_t* e = stage + sbase;
+        uint32_t m = 0;
+        for (uint32_t xx = 0; xx < c; ++xx) {   // the three ranges as one index space
+          const int tt = (int)xx + (xx < c0 ? o0 : (xx < c01 ? o1 : o2));
+          const int2 u = vq2[tt];
+          const int l1 = (int)__sad(dy, u.x, __sad(dx, u.y, 0u));
+          if (l1 < tpsi) e[m++] = (uint16_t)((uint32_t)kq3[tt] | ((uint32_t)l1 << 12));
         }
+        if (m > (uint32_t)kMaxList) {
+          misc[1] = 1;
+          m = kMaxList;
+        }
+        ln[j] = (uint16_t)m;
+        so[j] = (uint16_t)sbase;
+        rk[j] = (uint16_t)atomicAdd(&hist[m], 1u);
+      }
+    }
+    __syncthreads();
+
+    // 4. labels in order of decreasing list length (warp 0): start[m] = number of labels with a longer list;
+    //    roff[r] = sum_{r' < r} (labels with list longer than r') = sum_{r' < r} start[r'];  arena allocation
+    if (t < 32) {
+      bool ok = misc[1] == 0;
+      const uint32_t h0 = hist[4 * lane], h1 = hist[4 * lane + 1], h2 = hist[4 * lane + 2], h3 = hist[4 * lane + 3];
+      const uint32_t hs = h0 + h1 + h2 + h3;
+      uint32_t suf = hs;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t u = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += u;
+      }
+      const uint32_t s3 = suf - hs, s2 = s3 + h3, s1 = s2 + h2, s0_ = s1 + h1;   // start of bins 4*lane+3 .. 4*lane
+      start[4 * lane] = s0_;
+      start[4 * lane + 1] = s1;
+      start[4 * lane + 2] = s2;
+      start[4 * lane + 3] = s3;
+      const int top = h3 ? 4 * lane + 3 : h2 ? 4 * lane + 2 : h1 ? 4 * lane + 1 : h0 ? 4 * lane : 0;
+      const int nr = __reduce_max_sync(0xffffffffu, top);                        // longest list
+      const uint32_t ls = s0_ + s1 + s2 + s3;
+      uint32_t pre = ls;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t u = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += u;
+      }
+      pre -= ls;
+      roff[4 * lane] = (uint16_t)pre;
+      roff[4 * lane + 1] = (uint16_t)(pre + s0_);
+      roff[4 * lane + 2] = (uint16_t)(pre + s0_ + s1);
+      roff[4 * lane + 3] = (uint16_t)(pre + s0_ + s1 + s2);
+      __syncwarp();
+      const uint32_t total = roff[nr];
+      const uint32_t so_b = (uint32_t)(kRecHeader + ((2 * (nr + 1) + 7) & ~7));
+      const uint32_t eo_b = so_b + 8u * (uint32_t)n;
+      const unsigned long long bytes = ((unsigned long long)eo_b + 2ull * total + 15ull) & ~15ull;
+      unsigned long long off = 0;
+      ok = ok && bytes <= slot_bytes;
+      if (ok) {
+        if (lane == 0) off = atomicAdd(cursor, bytes);
+        off = __shfl_sync(0xffffffffu, off, 0);
+        ok = off + bytes <= arena_bytes;
       }
       if (lane == 0) {
-        uint32_t* h = reinterpret_cast<uint32_t*>(rec);
-        h[0] = (uint32_t)n;
-        h[1] = total;
-        h[2] = 0;
-        h[3] = 0;
+        misc[2] = (uint32_t)nr;
+        misc[3] = ok ? 1u : 0u;
+        misc[4] = (uint32_t)off;
+        misc[5] = (uint32_t)(off >> 32);
+        misc[6] = so_b;
+        misc[7] = eo_b;
+        desc[task] = ok ? ((off >> 4) | ((bytes >> 4) << 40)) : 0ull;
+        if (ok) {
+          uint32_t* h = reinterpret_cast<uint32_t*>(arena + off);
+          h[0] = (uint32_t)n;
+          h[1] = (uint32_t)nr;
+          h[2] = so_b;
+          h[3] = eo_b;
+        }
       }
     }
-    if (lane == 0) desc[task] = ok ? ((off >> 4) | ((bytes >> 4) << 40)) : 0ull;
-    // empty the touched buckets for the next record
-    __syncwarp();
-    for (int s = lane; s < nq; s += 32) rng[bucket_key(vq[s], bshift)] = kRngEmpty;
-    __syncwarp();
+    __syncthreads();
+    const bool ok = misc[3] != 0;
+    if (ok) {
+      // 5. position of every label
+      for (int j = t; j < n; j += kBuildThreads) inv[start[ln[j]] + rk[j]] = (uint16_t)j;
+      __syncthreads();
+      // 6. write the record
+      const int nr = (int)misc[2];
+      unsigned char* rec = arena + (((unsigned long long)misc[5] << 32) | misc[4]);
+      uint16_t* ro_g = reinterpret_cast<uint16_t*>(rec + kRecHeader);
+      for (int r = t; r <= nr; r += kBuildThreads) ro_g[r] = (uint16_t)(2u * roff[r]);
+      uint2* st = reinterpret_cast<uint2*>(rec + misc[6]);
+      uint16_t* ents = reinterpret_cast<uint16_t*>(rec + misc[7]);
+      for (int pos = t; pos < n; pos += kBuildThreads) {
+        const int j = inv[pos];
+        const int len = ln[j];
+        const uint16_t* src = stage + so[j];
+        st[pos] = make_uint2((uint32_t)vp[j], (uint32_t)cq[j] | ((uint32_t)j << 16) | ((uint32_t)len << 25));
+        for (int r = 0; r < len; ++r) ents[roff[r] + pos] = src[r];
+      }
+    }
+    // 7. empty the touched buckets and the per-record state for the next record
+    for (int s = t; s < nq; s += kBuildThreads) {
+      const int2 u = vq2[s];
+      rng[(bkt_y(u.x >> bshift) << 6) | bkt_x(u.y >> bshift)] = kRngEmpty;
+    }
+    if (t < 2) misc[t] = 0;
+    __syncthreads();
   }
-  (void)ln;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -313,27 +437,29 @@ struct ChainArgs {
   uint16_t* bp;
   const unsigned long long* desc;
   const unsigned char* arena;
-  int H, W, K, Kpad, phase, tpsi, shift, nslots;
+  int H, W, K, Kpad, phase, tpsi, shift, slot_shift;   // 1 << slot_shift slots
   uint32_t slot_bytes;
   double lamda;
 };
 
 // Returns true (uniformly) when a narrow run overflowed and nothing was written.
 template <bool Wide, typename CostT, int T>
-__device__ __forceinline__ bool chain_body(const ChainArgs& a, unsigned char* smem_raw) {
+__device__ __forceinline__ bool chain_body(const ChainArgs& a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   using Key = typename KeyOf<Wide>::type;
   const Key INF = key_inf<Wide>();
   const ChainGeom g = chain_geom(a.phase, blockIdx.x, a.H, a.W);
-  const int t = threadIdx.x, lane = t & 31;
-  const int K = a.K, Kpad = a.Kpad, S = a.nslots, shift = a.shift, tpsi = a.tpsi;
+  const int t = threadIdx.x, lane = t & 31, wfirst = t & ~31;
+  const int K = a.K, Kpad = a.Kpad, shift = a.shift, tpsi = a.tpsi;
+  const int S = 1 << a.slot_shift, smask = S - 1;
   const int orient = a.phase & 1;
   const unsigned long long* dsc = a.desc + (size_t)orient * a.H * a.W;
   const CostT* cost = static_cast<const CostT*>(a.cost);
 
-  // shared memory: mbar[4] | present[4] | trunc[3] (+pad) | rep[2][Kpad] | oldvec[len] | vprev[Kpad] | slots
+  // shared memory: mbar[4] | present[4] | trunc[4] | rep[2][Kpad] | oldvec[len] | vprev[Kpad] | slots
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* present_s = reinterpret_cast<uint32_t*>(smem_raw + 32);
-  Key* trunc_s = reinterpret_cast<Key*>(smem_raw + 48);                       // 3 keys (<= 24 bytes) + pad -> 80
+  Key* trunc_s = reinterpret_cast<Key*>(smem_raw + 48);                       // 4 keys (<= 32 bytes)
   Key* rep_s = reinterpret_cast<Key*>(smem_raw + 80);
   int32_t* oldvec = reinterpret_cast<int32_t*>(smem_raw + 80 + 2 * (size_t)Kpad * 8);   // sized for wide keys
   int32_t* vprev = oldvec + g.len;
@@ -346,7 +472,7 @@ __device__ __forceinline__ bool chain_body(const ChainArgs& a, unsigned char* sm
     const int p = pixel(i);
     oldvec[i] = a.pvec[(size_t)p * K + a.labels[p]];
   }
-  if (t < 3) trunc_s[t] = INF;
+  if (t < 4) trunc_s[t] = INF;
   if (t == 0) {
     for (int s = 0; s < S; ++s) ptx::mbar_init(&mbar[s], 1);
     ptx::fence_barrier_init();
@@ -356,7 +482,7 @@ __device__ __forceinline__ bool chain_body(const ChainArgs& a, unsigned char* sm
   // producer (thread 0): record i goes to slot i % S; absent records complete their barrier phase without bytes
   unsigned long long d_next = 0;
   auto issue = [&](int i, unsigned long long d) {
-    const int slot = i % S;
+    const int slot = i & smask;
     const uint32_t bytes = (uint32_t)(d >> 40) << 4;
     present_s[slot] = bytes;
     if (bytes) {
@@ -371,62 +497,76 @@ __device__ __forceinline__ bool chain_body(const ChainArgs& a, unsigned char* sm
     if (S < g.len) d_next = dsc[pixel(S)];
   }
 
-  uint16_t* bp_chain = a.bp + (size_t)blockIdx.x * g.len * Kpad;
+  uint16_t* bp_row = a.bp + (size_t)blockIdx.x * g.len * Kpad;   // row of step i (advanced every step)
   const uint32_t tpsi_dp = (uint32_t)tpsi << shift;
+  const uint32_t l1_mult = 1u << (shift + kLabelBits - 12);   // narrow keys: (L1 << 12) * l1_mult = L1 << (shift + 9)
   uint32_t ovf = 0;
 
-  for (int i = 0; i < g.len; ++i) {
-    const int slot = i % S;
-    ptx::mbar_wait(&mbar[slot], (uint32_t)(i / S) & 1u);
+  for (int i = 0; i < g.len; ++i, bp_row += Kpad) {
+    const int slot = i & smask;
+    ptx::mbar_wait(&mbar[slot], (uint32_t)(i >> a.slot_shift) & 1u);
     const uint32_t present = present_s[slot];
-    const Key* rp = rep_s + ((i & 1) ^ 1) * Kpad;
-    Key* rc = rep_s + (i & 1) * Kpad;
-    const Key trunc_prev = trunc_s[(i + 2) % 3];
-    // unary side terms (sidepsi :84-88): the chain's own neighbours with their labels from before this call
-    const int32_t ov_a = i + 1 < g.len ? oldvec[i + 1] : 0, ov_b = i > 0 ? oldvec[i - 1] : 0;
+    // rep_s[2 * k + b]: key of label k of the pixel visited at a step of parity b (the two buffers are interleaved so
+    // that an entry's byte offset and the buffer select combine in one logic operation)
+    const uint32_t prv_off = (uint32_t)((i & 1) ^ 1) * (uint32_t)sizeof(Key);
+    const unsigned char* rpb = reinterpret_cast<const unsigned char*>(rep_s);
+    Key* rc = rep_s + (i & 1);
     Key key = INF;
     if (present) {
       const unsigned char* rec = slots + (size_t)slot * a.slot_bytes;
-      const int n = (int)*reinterpret_cast<const uint32_t*>(rec);
-      if (t < n) {
-        const uint32_t* st = reinterpret_cast<const uint32_t*>(rec + kRecHeader) + 3 * t;
-        const int32_t v = (int32_t)st[0];
-        const uint32_t co = st[1], ol = st[2];
-        const uint32_t orig = co & 1023u;
-        const int dy = vec_dy(v), dx = vec_dx(v);
-        uint32_t psi = 0;
-        if (i + 1 < g.len) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, ov_a));
-        if (i > 0) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, ov_b));
-        const uint32_t U = (co >> 10) + (psi << shift);
-        uint32_t dp = U;
-        if (i > 0) {
-          const int len = (int)(ol & 1023u);
-          const uint16_t* e = reinterpret_cast<const uint16_t*>(rec + kRecHeader + 12 * (size_t)n) + (ol >> 10);
-          Key acc = len ? INF : trunc_prev;   // quirk Q1: the truncation candidate only when the K-set is empty
-          Key acc1 = INF, acc2 = INF, acc3 = INF;
-          const int last = len - 1;
-          for (int x = 0; x < len; x += 4) {
-            const uint32_t e0 = e[x], e1 = e[min(x + 1, last)], e2 = e[min(x + 2, last)], e3 = e[min(x + 3, last)];
-            const Key c0 = key_add<Wide>(rp[e0 & 1023u], (e0 >> 10) << shift);
-            const Key c1 = key_add<Wide>(rp[e1 & 1023u], (e1 >> 10) << shift);
-            const Key c2 = key_add<Wide>(rp[e2 & 1023u], (e2 >> 10) << shift);
-            const Key c3 = key_add<Wide>(rp[e3 & 1023u], (e3 >> 10) << shift);
-            acc = min(acc, c0);
-            acc1 = min(acc1, c1);
-            acc2 = min(acc2, c2);
-            acc3 = min(acc3, c3);
+      const uint4 hdr = *reinterpret_cast<const uint4*>(rec);
+      const int n = (int)hdr.x;
+      if (wfirst < n) {   // warps without labels only take part in the barrier
+        const Key trunc_prev = trunc_s[(i + 3) & 3];
+        // unary side terms (sidepsi :84-88): the chain's own neighbours with their labels from before this call
+        const int32_t ov_a = i + 1 < g.len ? oldvec[i + 1] : 0, ov_b = i > 0 ? oldvec[i - 1] : 0;
+        if (t < n) {
+          const uint2 st = *reinterpret_cast<const uint2*>(rec + hdr.z + 8 * t);
+          const int32_t v = (int32_t)st.x;
+          const uint32_t pk = st.y;
+          const uint32_t orig = (pk >> 16) & 511u;
+          const int dy = vec_dy(v), dx = vec_dx(v);
+          uint32_t psi = 0;
+          if (i + 1 < g.len) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, ov_a));
+          if (i > 0) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, ov_b));
+          const uint32_t U = (pk & 0xFFFFu) + (psi << shift);
+          uint32_t dp = U;
+          if (i > 0) {
+            const int len = (int)(pk >> 25);
+            const uint16_t* roff = reinterpret_cast<const uint16_t*>(rec + kRecHeader);
+            const unsigned char* ents = rec + hdr.w + 2 * t;
+            Key acc = len ? INF : trunc_prev;   // quirk Q1: the truncation candidate only when the K-set is empty
+            Key acc1 = INF;
+            auto cand = [&](uint32_t e) -> Key {
+              const Key k = *reinterpret_cast<const Key*>(rpb + ((((e & 0xFF8u) << (Wide ? 1 : 0))) | prv_off));
+              if constexpr (Wide) return key_add<Wide>(k, (e >> 12) << shift);
+              else return k + (e & 0x7000u) * l1_mult;
+            };
+            int r = 0;
+            for (; r + 1 < len; r += 2) {
+              const uint32_t e0 = *reinterpret_cast<const uint16_t*>(ents + roff[r]);
+              const uint32_t e1 = *reinterpret_cast<const uint16_t*>(ents + roff[r + 1]);
+              acc = min(acc, cand(e0));
+              acc1 = min(acc1, cand(e1));
+            }
+            if (r < len) acc1 = min(acc1, cand(*reinterpret_cast<const uint16_t*>(ents + roff[r])));
+            acc = min(acc, acc1);
+            if constexpr (Wide) dp = key_dp<Wide>(acc) + U;
+            else dp = key_dp<Wide>(acc) - (key_dp<Wide>(trunc_prev) - tpsi_dp) + U;
+            bp_row[orig] = (uint16_t)key_label<Wide>(acc);
           }
-          acc = min(min(acc, acc1), min(acc2, acc3));
-          if constexpr (Wide) dp = key_dp<Wide>(acc) + U;
-          else dp = key_dp<Wide>(acc) - (key_dp<Wide>(trunc_prev) - tpsi_dp) + U;
-          bp_chain[(size_t)i * Kpad + orig] = (uint16_t)key_label<Wide>(acc);
+          if constexpr (!Wide) ovf |= dp >> 22;
+          key = make_key<Wide>(dp, orig);
+          rc[2 * orig] = key;
         }
-        if constexpr (!Wide) ovf |= dp >> 22;
-        key = make_key<Wide>(dp, orig);
-        rc[orig] = key;
+        // block minimum of (dp + tpsi, label) for the next step's truncation candidate (:152-157), lowest label on ties
+        const Key wmin = warp_min_key(key);
+        if (lane == 0 && wmin != INF) atomicMin(&trunc_s[i & 3], key_add<Wide>(wmin, tpsi_dp));
       }
     } else {
       // dense step: the record was not stored; evaluate the K-set from the proposal arrays
+      const Key trunc_prev = trunc_s[(i + 3) & 3];
+      const int32_t ov_a = i + 1 < g.len ? oldvec[i + 1] : 0, ov_b = i > 0 ? oldvec[i - 1] : 0;
       const int p = pixel(i);
       const int n = a.nprop[p];
       int nq = 0;
@@ -446,24 +586,24 @@ __device__ __forceinline__ bool chain_body(const ChainArgs& a, unsigned char* sm
         uint32_t dp = U;
         if (i > 0) {
           Key acc = INF;
+          const Key* rp = rep_s + ((i & 1) ^ 1);
           for (int k = 0; k < nq; ++k) {
             const int l1 = l1_vec(dy, dx, vprev[k]);
-            if (l1 < tpsi) acc = min(acc, key_add<Wide>(rp[k], (uint32_t)l1 << shift));
+            if (l1 < tpsi) acc = min(acc, key_add<Wide>(rp[2 * k], (uint32_t)l1 << shift));
           }
           if (acc == INF) acc = trunc_prev;
           if constexpr (Wide) dp = key_dp<Wide>(acc) + U;
           else dp = key_dp<Wide>(acc) - (key_dp<Wide>(trunc_prev) - tpsi_dp) + U;
-          bp_chain[(size_t)i * Kpad + t] = (uint16_t)key_label<Wide>(acc);
+          bp_row[t] = (uint16_t)key_label<Wide>(acc);
         }
         if constexpr (!Wide) ovf |= dp >> 22;
         key = make_key<Wide>(dp, (uint32_t)t);
-        rc[t] = key;
+        rc[2 * t] = key;
       }
+      const Key wmin = warp_min_key(key);
+      if (lane == 0 && wmin != INF) atomicMin(&trunc_s[i & 3], key_add<Wide>(wmin, tpsi_dp));
     }
-    // block minimum of (dp + tpsi, label) for the next step's truncation candidate (:152-157), lowest label on ties
-    const Key wmin = warp_min_key(key);
-    if (lane == 0 && wmin != INF) atomicMin(&trunc_s[i % 3], key_add<Wide>(wmin, tpsi_dp));
-    if (t == 0) trunc_s[(i + 1) % 3] = INF;
+    if (t == 0) trunc_s[(i + 1) & 3] = INF;   // written at step i+1, last read at step i-2
     __syncthreads();
     if (t == 0 && i + S < g.len) {
       issue(i + S, d_next);
@@ -484,10 +624,11 @@ __device__ __forceinline__ bool chain_body(const ChainArgs& a, unsigned char* sm
 
   // final label: lowest-index argmin of dp_last (:231-237) = label field of the last block minimum; backtrack
   // (:238-253) through the back-pointers, staged through shared memory a segment of rows at a time
-  int lab = (int)key_label<Wide>(trunc_s[(g.len - 1) % 3]);
+  int lab = (int)key_label<Wide>(trunc_s[(g.len - 1) & 3]);
   const int rows_cap = max(1, (int)(((size_t)S * a.slot_bytes) / ((size_t)Kpad * 2)));
   uint16_t* seg = reinterpret_cast<uint16_t*>(slots);
   const int vec_per_row = Kpad / 8;   // uint4 = 8 back-pointers
+  const uint16_t* bp_chain = a.bp + (size_t)blockIdx.x * g.len * Kpad;
   for (int hi = g.len - 1; hi >= 1; hi -= rows_cap) {
     const int lo = max(1, hi - rows_cap + 1);
     const int nrow = hi - lo + 1;
@@ -509,13 +650,14 @@ __device__ __forceinline__ bool chain_body(const ChainArgs& a, unsigned char* sm
 
 template <typename CostT, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) kset_chain_kernel(const ChainArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  if (!chain_body<false, CostT, T>(a, smem_raw)) return;
-  chain_body<true, CostT, T>(a, smem_raw);
+  if constexpr (kNarrowFirst) {
+    if (!chain_body<false, CostT, T>(a)) return;
+  }
+  chain_body<true, CostT, T>(a);
 }
 
 struct KsetLayout {
-  size_t bp, sorig, desc, cursor, arena, arena_bytes, total;
+  size_t bp, sorig, svec, desc, cursor, arena, arena_bytes, total;
   int Kst, Kpad;
 };
 
@@ -533,12 +675,13 @@ KsetLayout kset_layout(int H, int W, int K, size_t workspace_bytes) {
   };
   L.bp = take((col > row ? col : row) * L.Kpad * sizeof(uint16_t));
   L.sorig = take(n * L.Kst * sizeof(uint16_t));
+  L.svec = take(n * L.Kst * sizeof(int32_t));
   L.desc = take(2 * n * sizeof(unsigned long long));
   L.cursor = take(256);
   L.arena = off;
   if (workspace_bytes == 0) {
-    // default budget: header + 12 B per label + room for ~10 candidate entries per label, per record
-    L.arena_bytes = 2 * n * (size_t)(kRecHeader + 12 * K + 20 * K);
+    // default budget: header + round offsets + 8 B per label + ~8 entries per label, per record
+    L.arena_bytes = 2 * n * (size_t)(kRecHeader + 64 + 8 * K + 16 * K);
   } else {
     L.arena_bytes = workspace_bytes > off ? (workspace_bytes - off) & ~(size_t)15 : 0;
   }
@@ -554,7 +697,7 @@ template <typename CostT>
 int launch_sweeps_ksets(const int32_t* pvec, const CostT* cost, const int32_t* nprop, int32_t* labels, int H, int W,
                         int K, double lamda, int tpsi, int shift, int sweeps, int32_t* labels_per_sweep,
                         void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  if (K > 512 || tpsi < 1 || tpsi > 8) return FLOWB200_EUNSUPPORTED;
+  if (K > 512 || tpsi < 1 || tpsi > 8 || shift < 3) return FLOWB200_EUNSUPPORTED;
   const KsetLayout L = kset_layout(H, W, K, workspace_bytes);
   if (workspace_bytes < L.arena) return FLOWB200_EWORKSPACE;
   char* ws = static_cast<char*>(workspace);
@@ -574,30 +717,31 @@ int launch_sweeps_ksets(const int32_t* pvec, const CostT* cost, const int32_t* n
   // ring of record slots: as many (<= 4) as keep `minb` chains per SM resident
   const int maxlen = H > W ? H : W;
   const size_t fixed = ((80 + 2 * (size_t)Kpad * 8 + 4 * (size_t)maxlen + 4 * (size_t)Kpad + 127) & ~(size_t)127);
-  uint32_t slot_bytes = (uint32_t)((kRecHeader + 12 * (size_t)Kpad + 24 * (size_t)Kpad + 127) & ~(size_t)127);
-  int nslots = kMaxSlots;
+  // a slot holds the largest record the build kernel can stage: header, round offsets, n structs, staged entries
+  uint32_t slot_bytes =
+      (uint32_t)((kRecHeader + 264 + 8 * (size_t)Kpad + 2 * (size_t)kStagePerLabel * Kpad + 127) & ~(size_t)127);
+  int slot_shift = 2;
   const size_t budget = (size_t)(227 * 1024) / minb - 1024;
-  while (nslots > 2 && fixed + (size_t)nslots * slot_bytes > budget) --nslots;
-  if (fixed + (size_t)nslots * slot_bytes > budget) {
-    // long chains (large images): fewer resident chains rather than smaller slots
-    if (fixed + 2 * (size_t)slot_bytes > (size_t)227 * 1024) return FLOWB200_EUNSUPPORTED;
-  }
-  const size_t smem = fixed + (size_t)nslots * slot_bytes;
+  if (fixed + 4 * (size_t)slot_bytes > budget) slot_shift = 1;
+  // long chains (large images): fewer resident chains rather than smaller slots
+  if (fixed + ((size_t)slot_bytes << slot_shift) > (size_t)227 * 1024) return FLOWB200_EUNSUPPORTED;
+  const size_t smem = fixed + ((size_t)slot_bytes << slot_shift);
   FB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
   if (sweeps > 0) {
     uint16_t* sorig = reinterpret_cast<uint16_t*>(ws + L.sorig);
     unsigned long long* cursor = reinterpret_cast<unsigned long long*>(ws + L.cursor);
     FB_CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), stream));
+    int32_t* svec = reinterpret_cast<int32_t*>(ws + L.svec);
     kset_sort_kernel<<<min((npix + kSortWarps - 1) / kSortWarps, 8 * kNumSMs), kSortWarps * 32, 0, stream>>>(
-        pvec, nprop, npix, K, L.Kst, bshift, sorig);
+        pvec, nprop, npix, K, L.Kst, bshift, sorig, svec);
     FB_LAUNCH_CHECK();
-    const size_t bsmem = (size_t)kBuildWarps * ((size_t)kHashSize * 4 + (size_t)Kpad * 12);
+    const size_t bsmem = build_smem_bytes(Kpad);
     auto bk = kset_build_kernel<CostT>;
     FB_CUDA_CHECK(cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
-    const int bctas = (int)(227 * 1024 / (bsmem + 1024));
-    bk<<<min((2 * npix + kBuildWarps - 1) / kBuildWarps, max(1, bctas) * kNumSMs), kBuildWarps * 32, bsmem, stream>>>(
-        pvec, cost, nprop, sorig, H, W, K, L.Kst, Kpad, tpsi, bshift, shift, lamda, slot_bytes,
+    const int bctas = std::min(16, (int)(227 * 1024 / (bsmem + 1024)));
+    bk<<<min(2 * npix, max(1, bctas) * kNumSMs), kBuildThreads, bsmem, stream>>>(
+        pvec, cost, nprop, sorig, svec, H, W, K, L.Kst, Kpad, tpsi, bshift, shift, lamda, slot_bytes,
         reinterpret_cast<unsigned char*>(ws + L.arena), (unsigned long long)L.arena_bytes, cursor,
         reinterpret_cast<unsigned long long*>(ws + L.desc));
     FB_LAUNCH_CHECK();
@@ -610,7 +754,7 @@ int launch_sweeps_ksets(const int32_t* pvec, const CostT* cost, const int32_t* n
   a.bp = reinterpret_cast<uint16_t*>(ws + L.bp);
   a.desc = reinterpret_cast<const unsigned long long*>(ws + L.desc);
   a.arena = reinterpret_cast<const unsigned char*>(ws + L.arena);
-  a.H = H; a.W = W; a.K = K; a.Kpad = Kpad; a.tpsi = tpsi; a.shift = shift; a.nslots = nslots;
+  a.H = H; a.W = W; a.K = K; a.Kpad = Kpad; a.tpsi = tpsi; a.shift = shift; a.slot_shift = slot_shift;
   a.slot_bytes = slot_bytes;
   a.lamda = lamda;
   for (int w = 0; w < sweeps; ++w) {
