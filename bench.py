@@ -325,7 +325,7 @@ def main():
             # per launch, as the contract asks: the dominant stage is a sequence of identical launches
             n_launch = {"bcd": directions * sweeps * 4, "knn": directions, "daisy": 2, "random": directions,
                         "consistency": 1}[dom]
-            kname = {"bcd": "bcd_chain_kernel", "knn": "knn_select_kernel (+ re-rank)", "daisy": "daisy kernels",
+            kname = {"bcd": "kset_chain_kernel", "knn": "knn_select_kernel (+ re-rank)", "daisy": "daisy kernels",
                      "random": "random_proposals_kernel", "consistency": "consistency_kernel"}[dom]
             traffic = None
             tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
@@ -339,7 +339,7 @@ def main():
                     "peak_source": pk["src"] + " (MEASURED_PEAKS.json)", "launches_per_step": n_launch,
                     "algorithmic_per_launch": amount / n_launch, "ms_per_launch": stages[dom] / n_launch,
                     "note": "stage time by CUDA events around the stage's C-ABI call on the launching stream"
-                            + ("; includes bcd_sort_kernel once per direction" if dom == "bcd" else ""),
+                            + ("; includes kset_sort_kernel and kset_build_kernel once per direction" if dom == "bcd" else ""),
                     "stage_ms": {k: round(v, 4) for k, v in stages.items()},
                     "stage_frac_of_roofline": {
                         k: round((work[k][1] / (v / 1e3) / (1e9 if work[k][0] == "hbm" else 1e12)) /
