@@ -14,12 +14,11 @@
 //                      steps ahead; a step is: wait for the slot, min over the label's entry list of
 //                      rep[k] + (L1 << ..), add the unary term, publish the new key, one block barrier.
 //
-// Keys are 32 bit: (dp - running minimum) << 9 | label, so that "smallest dp, lowest label on ties" (np.argmin,
-// python bcd.py:155/:175/:234) is one integer minimum and the block reduction is one REDUX + one shared atomic.
-// Subtracting the previous step's minimum from every dp changes no comparison.  Because of quirk Q1 (the truncation
-// candidate is ignored when S_l is not empty, :170-176) the spread of dp over the labels of a pixel is not bounded
-// by a constant; a chain whose relative dp leaves 22 bits re-runs itself with 64-bit keys (dp << 32 | label, no
-// renormalisation) -- same code, template parameter Wide.
+// Keys are 64 bit (dp << 32 | label): "smallest dp, lowest label on ties" (np.argmin, python bcd.py:155/:175/:234) is
+// one minimum, taken with the fp64 min instruction (see Key below).  32-bit keys relative to the running minimum were
+// tried first: because of quirk Q1 (the truncation candidate is ignored when S_l is not empty, :170-176) the spread of
+// dp over the labels of a pixel is not bounded, ~5 % of the row chains of the bench workload overflowed 22 bits and had
+// to be re-run, and a phase lasts as long as its slowest chain.
 //
 // A record that does not fit (arena exhausted, larger than a slot, data cost out of 22 bits) gets descriptor 0 and
 // its step is evaluated densely from pvec/cost inside the chain kernel, so any workspace size gives the exact result.
@@ -34,13 +33,7 @@ namespace flowb200 {
 namespace {
 
 constexpr uint32_t kRngEmpty = 0x0000FFFFu;   // first = 0xFFFF, last+1 = 0
-constexpr int kLabelBits = 9;                 // K <= 512
-constexpr uint32_t kLabelMask = (1u << kLabelBits) - 1;
 constexpr int kRecHeader = 16;
-// Try 32-bit keys first and re-run a chain with 64-bit keys when its relative dp overflows.  Measured on the bench
-// workload: ~5 % of the row chains overflow (label clusters that stay 16 units per step worse than the best label,
-// which quirk Q1 keeps alive), and a phase lasts as long as its slowest chain, so the re-runs doubled the phase time.
-constexpr bool kNarrowFirst = false;
 
 __device__ __forceinline__ int cidx(int k) { return k + (k >> 5); }
 
@@ -109,7 +102,7 @@ kset_sort_kernel(const int32_t* __restrict__ pvec, const int32_t* __restrict__ n
 //            0 .. cnt_r-1 and entry r of position t sits at roff[r] + t (jagged-diagonal storage): the chain
 //            kernel's lanes read consecutive uint16 and the lanes of a warp have (almost) equal trip counts.
 //   structs  n x {int32 vector; uint32 data cost (16) | original label (9) << 16 | list length (7) << 25}
-//   entries  uint16 (k << 3) | (L1 << 12): previous-pixel label k (original index) and L1(v_l, u_k) < tpsi
+//   entries  uint16 (k << 4) | (L1 << 13): previous-pixel label k (original index) and L1(v_l, u_k) < tpsi
 //   (roff is stored in BYTES, i.e. doubled, so that the chain kernel adds it to a byte pointer)
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxList = 127;                  // list length field: 7 bits
@@ -215,7 +208,7 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
       for (int s = t; s < nq; s += kBuildThreads) {
         const int32_t v = svq[s];
         vq2[s] = make_int2(vec_dy(v), vec_dx(v));
-        kq3[s] = (uint16_t)((uint32_t)sq[s] << 3);
+        kq3[s] = (uint16_t)((uint32_t)sq[s] << 4);
       }
     }
     if (t < 128) hist[t] = 0;
@@ -285,7 +278,7 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
           const int tt = (int)xx + (xx < c0 ? o0 : (xx < c01 ? o1 : o2));
           const int2 u = vq2[tt];
           const int l1 = (int)__sad(dy, u.x, __sad(dx, u.y, 0u));
-          if (l1 < tpsi) e[m++] = (uint16_t)((uint32_t)kq3[tt] | ((uint32_t)l1 << 12));
+          if (l1 < tpsi) e[m++] = (uint16_t)((uint32_t)kq3[tt] | ((uint32_t)l1 << 13));
         }
         if (m > (uint32_t)kMaxList) {
           misc[1] = 1;
@@ -331,7 +324,8 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
       roff[4 * lane + 3] = (uint16_t)(pre + s0_ + s1 + s2);
       __syncwarp();
       const uint32_t total = roff[nr];
-      const uint32_t so_b = (uint32_t)(kRecHeader + ((2 * (nr + 1) + 7) & ~7));
+      const int ntab = ((nr + 1 + 3) & ~3) + 8;   // round offsets, zero padded (the chain kernel reads groups of four ahead)
+      const uint32_t so_b = (uint32_t)(kRecHeader + 2 * ntab);
       const uint32_t eo_b = so_b + 8u * (uint32_t)n;
       const unsigned long long bytes = ((unsigned long long)eo_b + 2ull * total + 15ull) & ~15ull;
       unsigned long long off = 0;
@@ -368,7 +362,8 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
       const int nr = (int)misc[2];
       unsigned char* rec = arena + (((unsigned long long)misc[5] << 32) | misc[4]);
       uint16_t* ro_g = reinterpret_cast<uint16_t*>(rec + kRecHeader);
-      for (int r = t; r <= nr; r += kBuildThreads) ro_g[r] = (uint16_t)(2u * roff[r]);
+      const int ntab = ((nr + 1 + 3) & ~3) + 8;
+      for (int r = t; r < ntab; r += kBuildThreads) ro_g[r] = r <= nr ? (uint16_t)(2u * roff[r]) : (uint16_t)0;
       uint2* st = reinterpret_cast<uint2*>(rec + misc[6]);
       uint16_t* ents = reinterpret_cast<uint16_t*>(rec + misc[7]);
       for (int pos = t; pos < n; pos += kBuildThreads) {
@@ -392,41 +387,22 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
 // ------------------------------------------------------------------------------------------------
 // chains
 // ------------------------------------------------------------------------------------------------
-template <bool Wide> struct KeyOf { using type = uint32_t; };
-template <> struct KeyOf<true> { using type = unsigned long long; };
+// Keys are 64 bit: dp << 32 | label, so that "smallest dp, lowest label on ties" (np.argmin, python bcd.py:155/:175/
+// :234) is one unsigned minimum (two compares + two selects; fmin on the bit patterns was tried and is worse: sm_100
+// has no DMNMX, it compiles to DSETP.MIN + selects + NaN quieting).
+using Key = unsigned long long;
+constexpr Key kKeyInf = ~0ull;
 
-template <bool Wide>
-__device__ __forceinline__ typename KeyOf<Wide>::type key_inf() {
-  if constexpr (Wide) return ~0ull;
-  else return 0xFFFFFFFFu;
-}
-// key of (dp, label); dp term d added to a key
-template <bool Wide>
-__device__ __forceinline__ typename KeyOf<Wide>::type make_key(uint32_t dp, uint32_t label) {
-  if constexpr (Wide) return ((unsigned long long)dp << 32) | label;
-  else return (dp << kLabelBits) | label;
-}
-template <bool Wide>
-__device__ __forceinline__ typename KeyOf<Wide>::type key_add(typename KeyOf<Wide>::type k, uint32_t d) {
-  if constexpr (Wide) return k + ((unsigned long long)d << 32);
-  else return k + (d << kLabelBits);
-}
-template <bool Wide>
-__device__ __forceinline__ uint32_t key_dp(typename KeyOf<Wide>::type k) {
-  if constexpr (Wide) return (uint32_t)(k >> 32);
-  else return k >> kLabelBits;
-}
-template <bool Wide>
-__device__ __forceinline__ uint32_t key_label(typename KeyOf<Wide>::type k) {
-  if constexpr (Wide) return (uint32_t)k;
-  else return k & kLabelMask;
-}
-__device__ __forceinline__ uint32_t warp_min_key(uint32_t k) { return __reduce_min_sync(0xffffffffu, k); }
-__device__ __forceinline__ unsigned long long warp_min_key(unsigned long long k) {
+__device__ __forceinline__ Key make_key(uint32_t dp, uint32_t label) { return ((Key)dp << 32) | label; }
+__device__ __forceinline__ Key key_add(Key k, uint32_t d) { return k + ((Key)d << 32); }
+__device__ __forceinline__ uint32_t key_dp(Key k) { return (uint32_t)(k >> 32); }
+__device__ __forceinline__ uint32_t key_label(Key k) { return (uint32_t)k; }
+__device__ __forceinline__ Key key_min(Key a, Key b) { return a < b ? a : b; }
+__device__ __forceinline__ Key warp_min_key(Key k) {
   const uint32_t hi = (uint32_t)(k >> 32), lo = (uint32_t)k;
   const uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
   const uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
-  return ((unsigned long long)mh << 32) | ml;
+  return ((Key)mh << 32) | ml;
 }
 
 struct ChainArgs {
@@ -442,12 +418,16 @@ struct ChainArgs {
   double lamda;
 };
 
-// Returns true (uniformly) when a narrow run overflowed and nothing was written.
-template <bool Wide, typename CostT, int T>
-__device__ __forceinline__ bool chain_body(const ChainArgs& a) {
+constexpr int kSlotSlack = 1024;   // masked lanes of the entry loop may read (and ignore) this far past a record
+
+__host__ __device__ inline size_t chain_fixed_smem(int Kpad, int len) {
+  // mbar[4] | present[4] | trunc[4] | rep[2 * Kpad] keys | oldvec[len] | vprev[Kpad]; slots follow, 128-aligned
+  return (80 + 2 * (size_t)Kpad * 8 + 4 * (size_t)len + 4 * (size_t)Kpad + 127) & ~(size_t)127;
+}
+
+template <typename CostT, int T>
+__device__ __forceinline__ void chain_body(const ChainArgs& a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  using Key = typename KeyOf<Wide>::type;
-  const Key INF = key_inf<Wide>();
   const ChainGeom g = chain_geom(a.phase, blockIdx.x, a.H, a.W);
   const int t = threadIdx.x, lane = t & 31, wfirst = t & ~31;
   const int K = a.K, Kpad = a.Kpad, shift = a.shift, tpsi = a.tpsi;
@@ -456,15 +436,13 @@ __device__ __forceinline__ bool chain_body(const ChainArgs& a) {
   const unsigned long long* dsc = a.desc + (size_t)orient * a.H * a.W;
   const CostT* cost = static_cast<const CostT*>(a.cost);
 
-  // shared memory: mbar[4] | present[4] | trunc[4] | rep[2][Kpad] | oldvec[len] | vprev[Kpad] | slots
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* present_s = reinterpret_cast<uint32_t*>(smem_raw + 32);
-  Key* trunc_s = reinterpret_cast<Key*>(smem_raw + 48);                       // 4 keys (<= 32 bytes)
+  Key* trunc_s = reinterpret_cast<Key*>(smem_raw + 48);
   Key* rep_s = reinterpret_cast<Key*>(smem_raw + 80);
-  int32_t* oldvec = reinterpret_cast<int32_t*>(smem_raw + 80 + 2 * (size_t)Kpad * 8);   // sized for wide keys
+  int32_t* oldvec = reinterpret_cast<int32_t*>(smem_raw + 80 + 2 * (size_t)Kpad * 8);
   int32_t* vprev = oldvec + g.len;
-  const size_t slots_off = (80 + 2 * (size_t)Kpad * 8 + 4 * (size_t)g.len + 4 * (size_t)Kpad + 127) & ~(size_t)127;
-  unsigned char* slots = smem_raw + slots_off;
+  unsigned char* slots = smem_raw + chain_fixed_smem(Kpad, g.len);
 
   auto pixel = [&](int i) { return (g.sy + i * g.ystep) * a.W + (g.sx + i * g.xstep); };
 
@@ -472,7 +450,7 @@ __device__ __forceinline__ bool chain_body(const ChainArgs& a) {
     const int p = pixel(i);
     oldvec[i] = a.pvec[(size_t)p * K + a.labels[p]];
   }
-  if (t < 4) trunc_s[t] = INF;
+  if (t < 4) trunc_s[t] = kKeyInf;
   if (t == 0) {
     for (int s = 0; s < S; ++s) ptx::mbar_init(&mbar[s], 1);
     ptx::fence_barrier_init();
@@ -499,8 +477,7 @@ __device__ __forceinline__ bool chain_body(const ChainArgs& a) {
 
   uint16_t* bp_row = a.bp + (size_t)blockIdx.x * g.len * Kpad;   // row of step i (advanced every step)
   const uint32_t tpsi_dp = (uint32_t)tpsi << shift;
-  const uint32_t l1_mult = 1u << (shift + kLabelBits - 12);   // narrow keys: (L1 << 12) * l1_mult = L1 << (shift + 9)
-  uint32_t ovf = 0;
+  const uint32_t l1_scale = 1u << shift;
 
   for (int i = 0; i < g.len; ++i, bp_row += Kpad) {
     const int slot = i & smask;
@@ -511,7 +488,7 @@ __device__ __forceinline__ bool chain_body(const ChainArgs& a) {
     const uint32_t prv_off = (uint32_t)((i & 1) ^ 1) * (uint32_t)sizeof(Key);
     const unsigned char* rpb = reinterpret_cast<const unsigned char*>(rep_s);
     Key* rc = rep_s + (i & 1);
-    Key key = INF;
+    Key key = kKeyInf;
     if (present) {
       const unsigned char* rec = slots + (size_t)slot * a.slot_bytes;
       const uint4 hdr = *reinterpret_cast<const uint4*>(rec);
@@ -533,35 +510,45 @@ __device__ __forceinline__ bool chain_body(const ChainArgs& a) {
           uint32_t dp = U;
           if (i > 0) {
             const int len = (int)(pk >> 25);
-            const uint16_t* roff = reinterpret_cast<const uint16_t*>(rec + kRecHeader);
+            // Entry r of this label sits at roff[r] + 2*t (bytes).  Four rounds at a time (their loads are independent);
+            // rounds >= len are masked: what they read is stale but in bounds (the round-offset table is zero padded
+            // by 8 entries and a slot is followed by kSlotSlack bytes).
+            const unsigned char* roff = rec + kRecHeader;
             const unsigned char* ents = rec + hdr.w + 2 * t;
-            Key acc = len ? INF : trunc_prev;   // quirk Q1: the truncation candidate only when the K-set is empty
-            Key acc1 = INF;
-            auto cand = [&](uint32_t e) -> Key {
-              const Key k = *reinterpret_cast<const Key*>(rpb + ((((e & 0xFF8u) << (Wide ? 1 : 0))) | prv_off));
-              if constexpr (Wide) return key_add<Wide>(k, (e >> 12) << shift);
-              else return k + (e & 0x7000u) * l1_mult;
+            auto load_e = [&](uint2 R, uint32_t (&e)[4]) {
+              e[0] = *reinterpret_cast<const uint16_t*>(ents + (R.x & 0xFFFFu));
+              e[1] = *reinterpret_cast<const uint16_t*>(ents + (R.x >> 16));
+              e[2] = *reinterpret_cast<const uint16_t*>(ents + (R.y & 0xFFFFu));
+              e[3] = *reinterpret_cast<const uint16_t*>(ents + (R.y >> 16));
             };
-            int r = 0;
-            for (; r + 1 < len; r += 2) {
-              const uint32_t e0 = *reinterpret_cast<const uint16_t*>(ents + roff[r]);
-              const uint32_t e1 = *reinterpret_cast<const uint16_t*>(ents + roff[r + 1]);
-              acc = min(acc, cand(e0));
-              acc1 = min(acc1, cand(e1));
+            Key acc0 = len ? kKeyInf : trunc_prev;   // quirk Q1: the truncation candidate only when the K-set is empty
+            Key acc1 = kKeyInf, acc2 = kKeyInf, acc3 = kKeyInf;
+            uint2 R = *reinterpret_cast<const uint2*>(roff);
+            for (int r = 0; r < len; r += 4) {
+              uint32_t e[4];
+              load_e(R, e);
+              R = *reinterpret_cast<const uint2*>(roff + 2 * r + 8);   // next group's round offsets
+              Key c[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {   // (k << 4) | buffer select = byte offset of rep_s[2 * k + b]
+                const uint2 kk = *reinterpret_cast<const uint2*>(rpb + ((e[j] & 0x1FF0u) | prv_off));
+                c[j] = make_key(kk.y + (e[j] >> 13) * l1_scale, kk.x);
+              }
+              acc0 = key_min(acc0, c[0]);
+              if (r + 1 < len) acc1 = key_min(acc1, c[1]);
+              if (r + 2 < len) acc2 = key_min(acc2, c[2]);
+              if (r + 3 < len) acc3 = key_min(acc3, c[3]);
             }
-            if (r < len) acc1 = min(acc1, cand(*reinterpret_cast<const uint16_t*>(ents + roff[r])));
-            acc = min(acc, acc1);
-            if constexpr (Wide) dp = key_dp<Wide>(acc) + U;
-            else dp = key_dp<Wide>(acc) - (key_dp<Wide>(trunc_prev) - tpsi_dp) + U;
-            bp_row[orig] = (uint16_t)key_label<Wide>(acc);
+            const Key acc = key_min(key_min(acc0, acc1), key_min(acc2, acc3));
+            dp = key_dp(acc) + U;
+            bp_row[orig] = (uint16_t)key_label(acc);
           }
-          if constexpr (!Wide) ovf |= dp >> 22;
-          key = make_key<Wide>(dp, orig);
+          key = make_key(dp, orig);
           rc[2 * orig] = key;
         }
         // block minimum of (dp + tpsi, label) for the next step's truncation candidate (:152-157), lowest label on ties
         const Key wmin = warp_min_key(key);
-        if (lane == 0 && wmin != INF) atomicMin(&trunc_s[i & 3], key_add<Wide>(wmin, tpsi_dp));
+        if (lane == 0 && wmin != kKeyInf) atomicMin(&trunc_s[i & 3], key_add(wmin, tpsi_dp));
       }
     } else {
       // dense step: the record was not stored; evaluate the K-set from the proposal arrays
@@ -585,25 +572,23 @@ __device__ __forceinline__ bool chain_body(const ChainArgs& a) {
         const uint32_t U = (uint32_t)quant_cost<CostT>(cost[(size_t)p * K + t], a.lamda, shift) + (psi << shift);
         uint32_t dp = U;
         if (i > 0) {
-          Key acc = INF;
+          Key acc = kKeyInf;
           const Key* rp = rep_s + ((i & 1) ^ 1);
           for (int k = 0; k < nq; ++k) {
             const int l1 = l1_vec(dy, dx, vprev[k]);
-            if (l1 < tpsi) acc = min(acc, key_add<Wide>(rp[2 * k], (uint32_t)l1 << shift));
+            if (l1 < tpsi) acc = key_min(acc, key_add(rp[2 * k], (uint32_t)l1 << shift));
           }
-          if (acc == INF) acc = trunc_prev;
-          if constexpr (Wide) dp = key_dp<Wide>(acc) + U;
-          else dp = key_dp<Wide>(acc) - (key_dp<Wide>(trunc_prev) - tpsi_dp) + U;
-          bp_row[t] = (uint16_t)key_label<Wide>(acc);
+          if (acc == kKeyInf) acc = trunc_prev;
+          dp = key_dp(acc) + U;
+          bp_row[t] = (uint16_t)key_label(acc);
         }
-        if constexpr (!Wide) ovf |= dp >> 22;
-        key = make_key<Wide>(dp, (uint32_t)t);
+        key = make_key(dp, (uint32_t)t);
         rc[2 * t] = key;
       }
       const Key wmin = warp_min_key(key);
-      if (lane == 0 && wmin != INF) atomicMin(&trunc_s[i & 3], key_add<Wide>(wmin, tpsi_dp));
+      if (lane == 0 && wmin != kKeyInf) atomicMin(&trunc_s[i & 3], key_add(wmin, tpsi_dp));
     }
-    if (t == 0) trunc_s[(i + 1) & 3] = INF;   // written at step i+1, last read at step i-2
+    if (t == 0) trunc_s[(i + 1) & 3] = kKeyInf;   // written at step i+1, last read at step i-2
     __syncthreads();
     if (t == 0 && i + S < g.len) {
       issue(i + S, d_next);
@@ -611,20 +596,9 @@ __device__ __forceinline__ bool chain_body(const ChainArgs& a) {
     }
   }
 
-  if constexpr (!Wide) {
-    if (__syncthreads_or((int)ovf)) {
-      // leave the barriers reusable for the wide re-run
-      if (t == 0)
-        for (int s = 0; s < S; ++s)
-          asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(ptx::smem_u32(&mbar[s])) : "memory");
-      __syncthreads();
-      return true;
-    }
-  }
-
   // final label: lowest-index argmin of dp_last (:231-237) = label field of the last block minimum; backtrack
   // (:238-253) through the back-pointers, staged through shared memory a segment of rows at a time
-  int lab = (int)key_label<Wide>(trunc_s[(g.len - 1) & 3]);
+  int lab = (int)key_label(trunc_s[(g.len - 1) & 3]);
   const int rows_cap = max(1, (int)(((size_t)S * a.slot_bytes) / ((size_t)Kpad * 2)));
   uint16_t* seg = reinterpret_cast<uint16_t*>(slots);
   const int vec_per_row = Kpad / 8;   // uint4 = 8 back-pointers
@@ -645,15 +619,11 @@ __device__ __forceinline__ bool chain_body(const ChainArgs& a) {
     __syncthreads();   // (uniform: lab is only meaningful in thread 0)
   }
   if (t == 0) a.labels[pixel(0)] = lab;
-  return false;
 }
 
 template <typename CostT, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) kset_chain_kernel(const ChainArgs a) {
-  if constexpr (kNarrowFirst) {
-    if (!chain_body<false, CostT, T>(a)) return;
-  }
-  chain_body<true, CostT, T>(a);
+  chain_body<CostT, T>(a);
 }
 
 struct KsetLayout {
@@ -697,7 +667,11 @@ template <typename CostT>
 int launch_sweeps_ksets(const int32_t* pvec, const CostT* cost, const int32_t* nprop, int32_t* labels, int H, int W,
                         int K, double lamda, int tpsi, int shift, int sweeps, int32_t* labels_per_sweep,
                         void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  if (K > 512 || tpsi < 1 || tpsi > 8 || shift < 3) return FLOWB200_EUNSUPPORTED;
+  if (K > 512 || tpsi < 1 || tpsi > 8) return FLOWB200_EUNSUPPORTED;
+  {   // dp is a uint32
+    const unsigned long long per_step = ((unsigned long long)(3 * tpsi) << shift) + 65535ull;
+    if ((unsigned long long)(H > W ? H : W) * per_step >= 0xFFFF0000ull) return FLOWB200_EUNSUPPORTED;
+  }
   const KsetLayout L = kset_layout(H, W, K, workspace_bytes);
   if (workspace_bytes < L.arena) return FLOWB200_EWORKSPACE;
   char* ws = static_cast<char*>(workspace);
@@ -716,10 +690,11 @@ int launch_sweeps_ksets(const int32_t* pvec, const CostT* cost, const int32_t* n
 
   // ring of record slots: as many (<= 4) as keep `minb` chains per SM resident
   const int maxlen = H > W ? H : W;
-  const size_t fixed = ((80 + 2 * (size_t)Kpad * 8 + 4 * (size_t)maxlen + 4 * (size_t)Kpad + 127) & ~(size_t)127);
+  // (masked lanes of the entry loop may also read up to 8272 bytes past the start of shared memory)
+  const size_t fixed = std::max(chain_fixed_smem(Kpad, maxlen) + kSlotSlack, (size_t)8448);
   // a slot holds the largest record the build kernel can stage: header, round offsets, n structs, staged entries
   uint32_t slot_bytes =
-      (uint32_t)((kRecHeader + 264 + 8 * (size_t)Kpad + 2 * (size_t)kStagePerLabel * Kpad + 127) & ~(size_t)127);
+      (uint32_t)((kRecHeader + 288 + 8 * (size_t)Kpad + 2 * (size_t)kStagePerLabel * Kpad + 127) & ~(size_t)127);
   int slot_shift = 2;
   const size_t budget = (size_t)(227 * 1024) / minb - 1024;
   if (fixed + 4 * (size_t)slot_bytes > budget) slot_shift = 1;
