@@ -127,8 +127,13 @@ int flowb200_quantise_costs(const float* lcost, int32_t* m, size_t n, double lam
 /* ---- A9-A11  bcd / ceoBCD  (python bcd.py:101-257, 261-284) ----
  * Runs `sweeps` sweeps of the four phases (even columns down, even rows right-to-left, odd columns up,
  * odd rows left-to-right) on `labels` in place.  cost: float32 / float64 / int32 [H][W][K] per bcd_mode.
- * labels_per_sweep (optional): int32 [sweeps][H][W] snapshot after every sweep (what ceoBCD saves). */
+ * labels_per_sweep (optional): int32 [sweeps][H][W] snapshot after every sweep (what ceoBCD saves).
+ * The int32 modes compile the K-sets S_l = {k : L1(v_l,u_k) < tpsi} of every (pixel, chain direction) once per call
+ * into sparse records in the workspace (the reference caches them too: pakovanje, daisy i flann.py:256-309) and the
+ * chains stream them; K-sets that do not fit are evaluated on the fly, so any workspace between
+ * flowb200_bcd_min_workspace_bytes() and flowb200_bcd_workspace_bytes() (the recommended size) gives the same labels. */
 size_t flowb200_bcd_workspace_bytes(int H, int W, int K);
+size_t flowb200_bcd_min_workspace_bytes(int H, int W, int K);
 int flowb200_bcd(const int32_t* pvec, const void* cost, const int32_t* nprop, int32_t* labels,
                  int H, int W, int K, int bcd_mode, double lamda, int tpsi, int cost_shift, int sweeps,
                  int32_t* labels_per_sweep, void* workspace, size_t workspace_bytes, flowb200_stream_t stream);

@@ -46,6 +46,7 @@ SYMBOLS = {
     "flowb200_ksets_pack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "flowb200_quantise_costs": (C.c_int, [_P, _P, C.c_size_t, C.c_double, C.c_int, _P]),
     "flowb200_bcd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "flowb200_bcd_min_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "flowb200_bcd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                C.c_int, _P, _P, C.c_size_t, _P]),
     "flowb200_flow_from_labels": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),

@@ -613,6 +613,12 @@ extern "C" size_t flowb200_bcd_workspace_bytes(int H, int W, int K) {
   return a > b ? a : b;
 }
 
+extern "C" size_t flowb200_bcd_min_workspace_bytes(int H, int W, int K) {
+  if (H <= 0 || W <= 0 || K <= 0) return 0;
+  const size_t a = legacy_workspace_bytes(H, W, K), b = ksets_min_workspace_bytes(H, W, K);
+  return a > b ? a : b;
+}
+
 extern "C" int flowb200_bcd(const int32_t* pvec, const void* cost, const int32_t* nprop, int32_t* labels, int H, int W,
                             int K, int bcd_mode, double lamda, int tpsi, int cost_shift, int sweeps,
                             int32_t* labels_per_sweep, void* workspace, size_t workspace_bytes,

@@ -48,5 +48,6 @@ int launch_sweeps_ksets(const int32_t* pvec, const CostT* cost, const int32_t* n
                         int K, double lamda, int tpsi, int shift, int sweeps, int32_t* labels_per_sweep,
                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t ksets_workspace_bytes(int H, int W, int K);
+size_t ksets_min_workspace_bytes(int H, int W, int K);   // fixed part only: every K-set is then evaluated densely
 
 }  // namespace flowb200

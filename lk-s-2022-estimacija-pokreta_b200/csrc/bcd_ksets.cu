@@ -662,6 +662,7 @@ KsetLayout kset_layout(int H, int W, int K, size_t workspace_bytes) {
 }  // namespace
 
 size_t ksets_workspace_bytes(int H, int W, int K) { return kset_layout(H, W, K, 0).total; }
+size_t ksets_min_workspace_bytes(int H, int W, int K) { return kset_layout(H, W, K, 0).arena; }
 
 template <typename CostT>
 int launch_sweeps_ksets(const int32_t* pvec, const CostT* cost, const int32_t* nprop, int32_t* labels, int H, int W,

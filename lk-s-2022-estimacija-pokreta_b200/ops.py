@@ -124,15 +124,15 @@ _BCD_COST_DTYPE = {_lib.BCD_FP64_F32COST: torch.float32, _lib.BCD_FP64_F64COST: 
 
 
 def bcd(pvec, cost, nprop, labels, sweeps, mode=_lib.BCD_FP64_F32COST, lamda=0.05, tpsi=8, cost_shift=12,
-        per_sweep=False):
+        per_sweep=False, workspace_bytes=None):
     """ceoBCD (python bcd.py:261-284): `sweeps` sweeps in place on labels.
 
     Returns int32 (sweeps,H,W) snapshots after every sweep when per_sweep, else None."""
     lib = _lib.load()
     H, W, K = pvec.shape
     snaps = torch.empty((sweeps, H, W), dtype=torch.int32, device=pvec.device) if per_sweep else None
-    nb = lib.flowb200_bcd_workspace_bytes(H, W, K)
-    ws = _workspace(nb, pvec.device)
+    nb = lib.flowb200_bcd_workspace_bytes(H, W, K) if workspace_bytes is None else int(workspace_bytes)
+    ws = _workspace(nb, pvec.device)[:nb]
     rc = lib.flowb200_bcd(_ptr(pvec, torch.int32, "pvec"), _ptr(cost, _BCD_COST_DTYPE[mode], "cost"),
                           _ptr(nprop, torch.int32, "nprop"), _ptr(labels, torch.int32, "labels"), H, W, K, int(mode),
                           float(lamda), int(tpsi), int(cost_shift), int(sweeps), _ptr(snaps), _ptr(ws), ws.numel(),

@@ -289,6 +289,24 @@ def test_bcd_vs_oracle_random(H, W, K):
         assert np.array_equal(snaps[0], want[0]) and np.array_equal(snaps[1], want[1]), mode
 
 
+@pytest.mark.parametrize("extra", [0, 40 << 10, 400 << 10])
+def test_bcd_int32_any_workspace_size(extra):
+    """The K-set records are a cache: with no room for them (every step evaluated densely) or room for only some of
+    them, the labels are the reference's (bcd_q12 fixture, unmodified `python bcd.py`)."""
+    ops, ioc, lib = pkg("ops"), pkg("io_contract"), pkg("_lib")
+    z = load_npz("bcd_q12")
+    sweeps, shift = int(z["meta"][5]), int(z["meta"][6])
+    pvec = dev(ioc.pack_proposals(z["proposals"]))
+    H, W, K = pvec.shape
+    nb = lib.load().flowb200_bcd_min_workspace_bytes(H, W, K) + extra
+    assert nb < lib.load().flowb200_bcd_workspace_bytes(H, W, K)
+    labels = dev(z["labels00"], torch.int32)
+    snaps = ops.bcd(pvec, dev(z["m"], torch.int32), dev(z["nprop"], torch.int32), labels, sweeps,
+                    mode=lib.BCD_INT32, cost_shift=shift, per_sweep=True, workspace_bytes=nb).cpu().numpy()
+    for w in range(sweeps):
+        assert np.array_equal(snaps[w], z[f"labels{w + 1:02d}"]), w
+
+
 def test_bcd_int32_on_float_costs_equals_quantise_then_int32():
     ops, ioc, lib = pkg("ops"), pkg("io_contract"), pkg("_lib")
     z = load_case("pair_a")

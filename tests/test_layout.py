@@ -45,6 +45,7 @@ def test_workspace_queries_without_gpu():
     assert 1 << 30 < n < 40 << 30
     assert L.flowb200_daisy_workspace_bytes(0, 5) == 0
     assert L.flowb200_bcd_workspace_bytes(436, 1024, 300) > 0
+    assert 0 < L.flowb200_bcd_min_workspace_bytes(436, 1024, 300) < L.flowb200_bcd_workspace_bytes(436, 1024, 300)
 
 
 def test_ops_refuse_cpu_tensors():
