@@ -37,6 +37,9 @@ WORKLOADS = {
     "1024x436_fwd_K150_bcd4": (436, 1024, 150, 4, 1),            # configs[0]
     "1024x436_fwdbwd_K300_bcd4": (436, 1024, 300, 4, 2),         # configs[1]  (metric is quoted on this)
     "1242x375_fwdbwd_K500_bcd8": (375, 1242, 500, 8, 2),         # configs[2]
+    # configs[4]: ONE pair on all ranks, target cells sharded, NCCL merge (huge.py); strong scaling
+    "3840x2160_huge_K150_bcd4": (2160, 3840, 150, 4, 2),
+    "1920x1080_huge_K150_bcd4": (1080, 1920, 150, 4, 2),
 }
 DEFAULT_WORKLOAD = "1024x436_fwdbwd_K300_bcd4"
 METRIC = "flow Mpix/s (DAISY+kNN+BCD+consistency)"
@@ -215,6 +218,102 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_huge(args):
+    """configs[4]: one image pair on all ranks (huge.flow_pair_sharded).  value = H*W / step time, strong scaling."""
+    import torch
+    import torch.distributed as dist
+    lib, ops, synth, huge = mod("_lib"), mod("ops"), mod("synth"), mod("huge")
+    lib.load()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W_ = max(args.warmup, 3)
+    p, sweeps, directions = make_params(args.workload, mod("params").DEFAULT_KNN_MODE)
+    bcd_mode = lib.BCD_INT32 if args.bcd_mode == "int32" else lib.BCD_FP64_F32COST
+    a, b, _, _ = synth.make_pair(p.H, p.W, 0)           # every rank holds the same pair
+    ha, hb = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+    g0, g1 = ha.cuda(), hb.cuda()
+    D = dist if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i, host=False):
+        x0, x1 = (ha.cuda(non_blocking=True), hb.cuda(non_blocking=True)) if host else (g0, g1)
+        out = huge.flow_pair_sharded(x0, x1, p, sweeps, directions, i, bcd_mode, rank, world, D)
+        return out.cpu() if host else out
+
+    for i in range(W_):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L0 = lib.load().flowb200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(W_ + i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.load().flowb200_launch_count() - L0
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i, host=True)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = p.H * p.W / 1e6 / (float(t.item()) / args.steps)
+    # the sharded stage alone (search + merge), CUDA events, max over ranks
+    d0, d1 = ops.daisy(g0), ops.daisy(g1)
+    barrier()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    huge.knn_proposals_sharded(d0, d1, p, rank, world, D)
+    k1.record()
+    barrier()
+    t = torch.tensor([k0.elapsed_time(k1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    knn_ms = float(t.item())
+    if rank == 0:
+        pk = peaks()
+        flops = algorithmic_work(p, sweeps, 1)["knn"][1]
+        ach = flops / (knn_ms / 1e3) / 1e12
+        line = {"metric": METRIC, "value": p.H * p.W / 1e6 / (ms_step / 1e3), "unit": "Mpix/s", "n_gpus": world,
+                "steps": args.steps, "warmup": W_, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "int32" if bcd_mode == lib.BCD_INT32 else "f64", "data": "synthetic",
+                "pairs_per_s": 1e3 / ms_step,
+                "config": {"workload": args.workload, "H": p.H, "W": p.W, "K": p.maxnprop, "k_cell": p.k_cell,
+                           "n_gauss": p.n_gauss, "bcd_times": sweeps, "directions": directions,
+                           "parallelism": f"1 pair, target cell columns sharded x{world}, broadcast merge; rest replicated",
+                           "l2": "working set (GBs of proposals) exceeds L2"},
+                "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * p.H * p.W * 3,
+                        "d2h_bytes_per_step": p.H * p.W * 12},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"kernel": "knn_select_kernel (+ re-rank, band merge)", "stage": "knn (one direction, sharded)",
+                             "bound": "tensor", "achieved": ach, "peak": pk["tensor"] * world, "unit": "TFLOP/s",
+                             "frac": ach / (pk["tensor"] * world), "traffic": None, "ms": knn_ms,
+                             "peak_source": pk["src"] + " (MEASURED_PEAKS.json) x n_gpus",
+                             "note": "algorithmic FLOPs of the full-image search / max-over-ranks time of search + merge"},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -229,6 +328,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if "huge" in args.workload:
+        return run_huge(args)
 
     import ctypes as C
     import torch

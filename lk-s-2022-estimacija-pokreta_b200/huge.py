@@ -1,0 +1,185 @@
+"""Single-huge-image mode (BASELINE.json configs[4]): one image pair on several GPUs.
+
+The proposal search is the part that shards: the TARGET cells are partitioned into contiguous bands of cell
+columns, one band per rank.  A rank searches only its band (plus nothing else: it crops the target descriptors to
+its band and the source descriptors to the columns whose +-cell_radius window reaches the band, and runs the
+ordinary per-cell exact search on that sub-image).  In the reference's slot order (daisy i flann.py:162-177: cell
+column major, cell row minor, then rank) the proposals one source pixel gets from one band are ONE contiguous slot
+range, so the "merge of per-GPU top-K lists" is not a comparison merge: every rank broadcasts its block and every
+rank copies slot ranges into place (`merge_bands`, NCCL over NVLink; gloo in the CPU tests).  Everything after the
+merge (random proposals, BCD, consistency) runs replicated on the merged proposal set, with identical results on
+every rank; splitting the BCD chains of a phase across ranks with a label all-gather per phase is the next step and
+not built yet.
+
+All functions here are host-side planning and torch.distributed plumbing; the arithmetic is the C-ABI kernels'.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+from .params import FlowParams
+
+
+@dataclass(frozen=True)
+class Band:
+    rank: int
+    ci_lo: int        # target cell columns [ci_lo, ci_hi) searched by this rank
+    ci_hi: int
+    sx0: int          # source columns [sx0, sx1) of the sub-image (sx0 is a multiple of cellw)
+    sx1: int
+    tx0: int          # target columns of the sub-image = the same [sx0, sx1): cells outside the band are searched
+    tx1: int          # too (halo, wasted) and their slots ignored by the merge
+
+    @property
+    def width(self):
+        return self.sx1 - self.sx0
+
+
+def band_plan(p: FlowParams, world: int):
+    """Contiguous, balanced bands of target cell columns.  Ranks beyond the number of cell columns get empty bands."""
+    n, R, cw = p.ncellx, p.cell_radius, p.cellw
+    bands = []
+    for r in range(world):
+        lo, hi = (n * r) // world, (n * (r + 1)) // world
+        if hi <= lo:
+            bands.append(Band(r, lo, lo, 0, 0, 0, 0))
+            continue
+        sx0 = max(0, lo - R) * cw
+        sx1 = min(p.W, (hi + R) * cw)
+        bands.append(Band(r, lo, hi, sx0, sx1, sx0, sx1))
+    return bands
+
+
+def sub_params(p: FlowParams, b: Band) -> FlowParams:
+    """Parameters of the rank's sub-image problem (full height, columns [sx0, sx1))."""
+    return p.with_shape(p.H, b.width)
+
+
+def _row_groups(p: FlowParams):
+    """Maximal runs of image rows whose number of cell rows in range is the same: [(y0, y1, n_cj)]."""
+    out = []
+    y = 0
+    while y < p.H:
+        r = y // p.cellh
+        n = max(0, min(p.ncelly - 1, r + p.cell_radius) - max(0, r - p.cell_radius) + 1)
+        y1 = min(p.H, (r + 1) * p.cellh)
+        if out and out[-1][2] == n:
+            out[-1] = (out[-1][0], y1, n)
+        else:
+            out.append((y, y1, n))
+        y = y1
+    return out
+
+
+def copy_plan(p: FlowParams, b: Band):
+    """Slot-range copies that place band `b`'s proposals into the full-image arrays:
+    [(y0, y1, x0, x1, dst_slot0, src_slot0, nslots)] with dst[y0:y1, x0:x1, dst_slot0:+n] = src[y0:y1, x0-sx0:x1-sx0,
+    src_slot0:+n].  Slot of the r-th neighbour from cell (ci, cj) at pixel (y, x): k*((ci-ci_min)*n_cj + (cj-cj_min)) + r
+    (SURVEY.md appendix A); n_cj and cj_min are the same in the sub-image (full height), ci_min differs."""
+    if b.ci_hi <= b.ci_lo:
+        return []
+    R, cw, k = p.cell_radius, p.cellw, p.k_cell
+    sub_c0 = b.sx0 // cw
+    plan = []
+    q_last = (p.W - 1) // cw
+    for q in range(q_last + 1):
+        x0, x1 = max(q * cw, b.sx0), min(min(p.W, (q + 1) * cw), b.sx1)
+        if x0 >= x1:
+            continue
+        g_lo, g_hi = max(0, q - R), min(p.ncellx - 1, q + R)
+        c_lo, c_hi = max(b.ci_lo, g_lo), min(b.ci_hi - 1, g_hi)
+        if c_lo > c_hi:
+            continue
+        s_lo = max(sub_c0, g_lo)
+        for y0, y1, n_cj in _row_groups(p):
+            if n_cj <= 0:
+                continue
+            plan.append((y0, y1, x0, x1, (c_lo - g_lo) * n_cj * k, (c_lo - s_lo) * n_cj * k, (c_hi - c_lo + 1) * n_cj * k))
+    return plan
+
+
+def nn_counts(p: FlowParams):
+    """nprop after generisi: k * (cell columns in range) * (cell rows in range), int32 (H, W)."""
+    R = p.cell_radius
+    qx = np.arange(p.W) // p.cellw
+    qy = np.arange(p.H) // p.cellh
+    nx = np.maximum(0, np.minimum(p.ncellx - 1, qx + R) - np.maximum(0, qx - R) + 1)
+    ny = np.maximum(0, np.minimum(p.ncelly - 1, qy + R) - np.maximum(0, qy - R) + 1)
+    return (p.k_cell * ny[:, None] * nx[None, :]).astype(np.int32)
+
+
+def merge_bands(p: FlowParams, bands, rank, sub_pvec, sub_lcost, device, dist=None, blocks=None):
+    """Every rank broadcasts its band block; every rank assembles the full proposal set.
+
+    sub_pvec int32 / sub_lcost float32: (H, band width, K) of THIS rank (None for an empty band).
+    blocks (tests): {rank: (pvec, lcost)} of the other ranks, instead of broadcasting.
+    Returns (pvec (H,W,K) int32 filled -1, lcost (H,W,K) float32 filled 1000, nprop int32, labels int32) where
+    labels is the first strict argmin of the data cost (daisy i flann.py:181-184)."""
+    import torch
+    H, W, K = p.H, p.W, p.maxnprop
+    pvec = torch.full((H, W, K), -1, dtype=torch.int32, device=device)
+    lcost = torch.full((H, W, K), 1000.0, dtype=torch.float32, device=device)
+    for b in bands:
+        if b.ci_hi <= b.ci_lo:
+            continue
+        if b.rank == rank:
+            bp, bc = sub_pvec.contiguous(), sub_lcost.contiguous()
+        elif blocks is not None:
+            bp, bc = blocks[b.rank]
+        else:
+            bp = torch.empty((H, b.width, K), dtype=torch.int32, device=device)
+            bc = torch.empty((H, b.width, K), dtype=torch.float32, device=device)
+        if dist is not None and blocks is None and len(bands) > 1:
+            dist.broadcast(bp, src=b.rank)
+            dist.broadcast(bc, src=b.rank)
+        for y0, y1, x0, x1, d0, s0, n in copy_plan(p, b):
+            pvec[y0:y1, x0:x1, d0:d0 + n] = bp[y0:y1, x0 - b.sx0:x1 - b.sx0, s0:s0 + n]
+            lcost[y0:y1, x0:x1, d0:d0 + n] = bc[y0:y1, x0 - b.sx0:x1 - b.sx0, s0:s0 + n]
+    nprop = torch.from_numpy(nn_counts(p)).to(device)
+    # first strict argmin: costs are >= 0, so the float bit pattern orders like the value; the slot breaks ties
+    labels = torch.empty((H, W), dtype=torch.int32, device=device)
+    slot = torch.arange(K, device=device, dtype=torch.int64)
+    for y0 in range(0, H, 128):   # row blocks bound the int64 temporary
+        key = (lcost[y0:y0 + 128].view(torch.int32).to(torch.int64) << 32) | slot
+        labels[y0:y0 + 128] = (key.min(dim=2).values & 0xFFFFFFFF).to(torch.int32)
+    labels = torch.where(nprop > 0, labels, torch.zeros_like(labels))
+    return pvec, lcost, nprop, labels
+
+
+def knn_proposals_sharded(desc_src, desc_tgt, p: FlowParams, rank, world, dist=None, knn_mode=None):
+    """generisi for one direction with the target cells sharded over `world` ranks.  Same outputs as
+    ops.knn_proposals on one device."""
+    from . import ops
+    bands = band_plan(p, world)
+    b = bands[rank]
+    sub_pvec = sub_lcost = None
+    if b.ci_hi > b.ci_lo:
+        sp = sub_params(p, b)
+        s = desc_src[:, b.sx0:b.sx1].contiguous()
+        t = desc_tgt[:, b.tx0:b.tx1].contiguous()
+        sub_pvec, sub_lcost, _, _ = ops.knn_proposals(s, t, sp, knn_mode=knn_mode)
+    return merge_bands(p, bands, rank, sub_pvec, sub_lcost, desc_src.device, dist)
+
+
+def flow_pair_sharded(bgr0, bgr1, p: FlowParams, sweeps, directions, seed, bcd_mode, rank, world, dist=None,
+                      want_raw=False):
+    """The whole path for ONE pair on `world` ranks: DAISY replicated, proposal search sharded by target cell band and
+    merged over `dist`, the rest replicated.  Returns what ops.flow_pair returns, identical on every rank."""
+    import torch
+    from . import ops, _lib
+    d = [ops.daisy(bgr0), ops.daisy(bgr1)]
+    uvv = []
+    for direction in range(directions):
+        src, tgt = d[direction], d[1 - direction]
+        pvec, lcost, nprop, labels = knn_proposals_sharded(src, tgt, p, rank, world, dist)
+        ops.random_proposals(src, tgt, p, pvec, lcost, nprop, labels, seed=seed + direction)
+        mode = _lib.BCD_INT32_F32COST if bcd_mode in (_lib.BCD_INT32, _lib.BCD_INT32_F32COST) else _lib.BCD_FP64_F32COST
+        ops.bcd(pvec, lcost, nprop, labels, sweeps, mode=mode, lamda=p.lamda, tpsi=p.tpsi, cost_shift=p.cost_shift)
+        uvv.append(ops.flow_from_labels(pvec, labels, want_yx=False)[1])
+        del pvec, lcost
+    out = uvv[0].clone()
+    if directions == 2:
+        ops.consistency(out, uvv[1], p.con_tresh)
+    if want_raw:
+        return out, uvv[0], (uvv[1] if directions == 2 else None)
+    return out

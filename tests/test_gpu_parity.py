@@ -4,6 +4,8 @@ Everything goes through the C ABI (libflowb200.so) via the package's ctypes laye
 bit-exact for labels, proposals, nprop, K-set bits, kNN indices, the consistency field and the
 float32 data costs; DAISY within 1e-4 relative to the per-descriptor maximum (north star).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -368,3 +370,59 @@ def test_pipeline_matches_stagewise_and_oracle():
     assert abs(e_got[0] - e_want[0]) <= 0.01, (e_got, e_want)       # north star: EPE within 0.01 px
     assert np.array_equal(raw_f.cpu().numpy(), ocons.ucitaj_flow(flows[0]))
     assert np.array_equal(out.cpu().numpy(), want)
+
+
+# ---------------------------------------------------------------- single-huge-image mode (SURVEY 8e, configs[4])
+@pytest.mark.parametrize("world", [2, 3])
+def test_banded_search_on_device_merges_to_full(world):
+    """Every band's search run on this one GPU in turn, merged with the slot-range copy plan: bit-identical to the
+    full-image search (proposals, costs, nprop, bestlabels)."""
+    ops, huge, params, synth = pkg("ops"), pkg("huge"), pkg("params"), pkg("synth")
+    H, W = 150, 584
+    p = params.for_k(150, H=H, W=W, knn_mode=1)
+    a, b, _, _ = synth.make_pair(H, W, 3)
+    d1, d2 = ops.daisy(dev(a)), ops.daisy(dev(b))
+    want = ops.knn_proposals(d1, d2, p)
+    bands = huge.band_plan(p, world)
+    blocks = {}
+    for bd in bands:
+        if bd.ci_hi > bd.ci_lo:
+            pv, lc, _, _ = ops.knn_proposals(d1[:, bd.sx0:bd.sx1].contiguous(), d2[:, bd.tx0:bd.tx1].contiguous(),
+                                             huge.sub_params(p, bd))
+            blocks[bd.rank] = (pv, lc)
+    for rank in range(world):
+        mine = blocks.get(rank, (None, None))
+        got = huge.merge_bands(p, bands, rank, mine[0], mine[1], d1.device, blocks=blocks)
+        for g, w in zip(got, want):
+            assert torch.equal(g, w)
+
+
+def test_two_ranks_nccl_flow_pair_equals_one_gpu(tmp_path):
+    """torchrun, 2 ranks over NCCL: the sharded pair pipeline returns, on both ranks, exactly what one GPU computes."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys, torch, torch.distributed as dist
+        sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+        from helpers import pkg
+        ops, huge, params, synth, lib = pkg("ops"), pkg("huge"), pkg("params"), pkg("synth"), pkg("_lib")
+        local = int(os.environ["LOCAL_RANK"]); torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        rank, world = dist.get_rank(), dist.get_world_size()
+        p = params.for_k(150, H=150, W=584, knn_mode=1)
+        a, b, _, _ = synth.make_pair(150, 584, 4)
+        g0, g1 = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        got = huge.flow_pair_sharded(g0, g1, p, 2, 2, 7, lib.BCD_INT32, rank, world, dist)
+        want = ops.flow_pair(g0, g1, p, 2, 2, seed=7, bcd_mode=lib.BCD_INT32)
+        ok = torch.equal(got, want)
+        open(os.path.join({str(tmp_path)!r}, f"ok{{rank}}"), "w").write(str(ok))
+        dist.destroy_process_group()
+    """))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29547", str(script)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert open(tmp_path / "ok0").read() == "True" and open(tmp_path / "ok1").read() == "True"

@@ -1,0 +1,89 @@
+"""Single-huge-image mode, host logic on CPU: banded proposal search + slot-range merge reproduces the full-image
+proposal set bit for bit (the CPU oracle stands in for the device search), in one process and over two gloo ranks."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from helpers import pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _descs(H, W, seed):
+    rng = np.random.default_rng(seed)
+    return (rng.random((H, W, 68), dtype=np.float32) * 0.05, rng.random((H, W, 68), dtype=np.float32) * 0.05)
+
+
+def _full(p, d1, d2):
+    from oracle import cport
+    prop, lc, npr, best = cport.generisi(d1, d2, p)
+    ioc = pkg("io_contract")
+    return ioc.pack_proposals(prop), lc.astype(np.float32), npr.astype(np.int32), best.astype(np.int32)
+
+
+def _band_block(p, b, d1, d2):
+    import torch
+    from oracle import cport
+    huge, ioc = pkg("huge"), pkg("io_contract")
+    sp = huge.sub_params(p, b)
+    prop, lc, _, _ = cport.generisi(d1[:, b.sx0:b.sx1], d2[:, b.tx0:b.tx1], sp)
+    return torch.from_numpy(ioc.pack_proposals(prop)), torch.from_numpy(lc.astype(np.float32))
+
+
+@pytest.mark.parametrize("H,W,cw,ch,R,k,world", [(40, 70, 8, 6, 2, 3, 2), (40, 70, 8, 6, 2, 3, 3), (33, 95, 9, 7, 1, 2, 4),
+                                                 (30, 26, 8, 6, 2, 2, 8), (36, 64, 8, 6, 2, 3, 1)])
+def test_banded_search_merges_to_full(H, W, cw, ch, R, k, world):
+    import torch
+    params, huge = pkg("params"), pkg("huge")
+    r = 2 * R + 1
+    p = params.FlowParams(H=H, W=W, cellw=cw, cellh=ch, cell_radius=R, k_cell=k, n_gauss=0, maxnprop=r * r * k + 3)
+    d1, d2 = _descs(H, W, H * W + world)
+    want = _full(p, d1, d2)
+    bands = huge.band_plan(p, world)
+    assert [b.ci_lo for b in bands][0] == 0 and bands[-1].ci_hi == p.ncellx
+    assert all(a.ci_hi == b.ci_lo for a, b in zip(bands, bands[1:]))
+    blocks = {b.rank: _band_block(p, b, d1, d2) for b in bands if b.ci_hi > b.ci_lo}
+    for rank in range(world):
+        mine = blocks.get(rank, (None, None))
+        pvec, lcost, nprop, labels = huge.merge_bands(p, bands, rank, mine[0], mine[1], "cpu", blocks=blocks)
+        assert np.array_equal(pvec.numpy(), want[0])
+        assert np.array_equal(lcost.numpy(), want[1])
+        assert np.array_equal(nprop.numpy(), want[2])
+        assert np.array_equal(labels.numpy(), want[3])
+
+
+def test_two_gloo_ranks_exchange_bands(tmp_path):
+    pytest.importorskip("torch")
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import importlib, os, sys
+        import numpy as np, torch, torch.distributed as dist
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, os.path.join({ROOT!r}, "tests"))
+        from helpers import pkg
+        from oracle import cport
+        params, huge, ioc = pkg("params"), pkg("huge"), pkg("io_contract")
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        p = params.FlowParams(H=40, W=70, cellw=8, cellh=6, cell_radius=2, k_cell=3, n_gauss=0, maxnprop=80)
+        rng = np.random.default_rng(5)
+        d1 = rng.random((40, 70, 68), dtype=np.float32) * 0.05
+        d2 = rng.random((40, 70, 68), dtype=np.float32) * 0.05
+        bands = huge.band_plan(p, world)
+        b = bands[rank]
+        prop, lc, _, _ = cport.generisi(d1[:, b.sx0:b.sx1], d2[:, b.tx0:b.tx1], huge.sub_params(p, b))
+        got = huge.merge_bands(p, bands, rank, torch.from_numpy(ioc.pack_proposals(prop)),
+                               torch.from_numpy(lc.astype(np.float32)), "cpu", dist=dist)
+        prop, lc, npr, best = cport.generisi(d1, d2, p)
+        ok = (np.array_equal(got[0].numpy(), ioc.pack_proposals(prop)) and np.array_equal(got[1].numpy(), lc.astype(np.float32))
+              and np.array_equal(got[2].numpy(), npr.astype(np.int32)) and np.array_equal(got[3].numpy(), best.astype(np.int32)))
+        open(os.path.join({str(tmp_path)!r}, f"ok{{rank}}"), "w").write(str(ok))
+    """))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+                       capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert open(tmp_path / "ok0").read() == "True" and open(tmp_path / "ok1").read() == "True"
