@@ -51,6 +51,12 @@ constexpr int kTmemCols = kAccStages * kTilesPerItem * kChunkN;   // 256: two CT
 constexpr int kSlabBytes = kTileM * 32;                  // one k16 block of 128 rows: 4096 B
 constexpr int kTileBytes = kKB * kSlabBytes;             // 20480 B
 constexpr int kListCap = 96;       // per-row candidate list in shared memory (compacted when > kListCap - 8)
+// Two passes over a cell's targets (the GEMM is recomputed; the tensor pipe is mostly idle anyway): pass 0 only
+// tracks the k smallest group minima (tau), pass 1 compares every score with the FINAL bound tau + 2 eps and
+// writes the few survivors straight to the candidate array.  No shared-memory lists, no compaction, ~3.6
+// instead of ~6.5 issue slots per score.  false = the single-pass streaming selection (kept for reference).
+constexpr bool kTwoPass = true;
+constexpr int kPasses = kTwoPass ? 2 : 1;
 constexpr int kCand = 32;          // candidates handed to the exact re-rank per (query, cell)
 constexpr int kSelThreads = 64 + 128 * kTilesPerItem;     // TMA warp, MMA warp, 4 epilogue warps per tile
 constexpr float kPadNorm = 60000.0f;   // n_hi of padding target rows: their score can never be selected
@@ -278,7 +284,8 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __re
           for (int kb = 0; kb < kKB; ++kb)
             ptx::tma_load_3d(sA + m * kTileBytes + kb * kSlabBytes, &tmap_q, &ss->a_full, kb * 16, qx0 + m * kTileW, qy0);
         }
-        for (int c = 0; c < nchunks; ++c, ++bcount) {
+        for (int cc = 0; cc < kPasses * nchunks; ++cc, ++bcount) {
+          const int c = cc % nchunks;
           const uint32_t st = bcount % kBStages, ph = (bcount / kBStages) & 1;
           ptx::mbar_wait_backoff(&ss->b_empty[st], ph ^ 1, 100);
           ptx::mbar_arrive_expect_tx(&ss->b_full[st], kTileBytes);
@@ -302,7 +309,7 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __re
         int cell, qx0, qy0, x1, y1;
         if (!decode_item(g, item, cell, qx0, qy0, x1, y1)) continue;
         ptx::mbar_wait_backoff(&ss->a_full, it & 1, 1000);
-        for (int c = 0; c < nchunks; ++c, ++bcount) {
+        for (int cc = 0; cc < kPasses * nchunks; ++cc, ++bcount) {
           const uint32_t st = bcount % kBStages, ph = (bcount / kBStages) & 1;
           const uint32_t acc = bcount % kAccStages, aph = (bcount / kAccStages) & 1;
           ptx::mbar_wait_backoff(&ss->b_full[st], ph, 100);
@@ -330,6 +337,127 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __re
     }
   } else {
     // ===================== selection epilogue =====================
+    if constexpr (kTwoPass) {
+      const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
+      const int mt = (warp - 2) >> 2;              // which of the item's tiles this warp serves
+      const int row = quad * 32 + lane;            // query row of the tile = TMEM lane
+      uint32_t bcount = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int cell, qx0, qy0, x1, y1;
+        if (!decode_item(g, item, cell, qx0, qy0, x1, y1)) continue;
+        const int px = qx0 + mt * kTileW + (row & (kTileW - 1)), py = qy0 + (row >> 4);
+        const bool valid = px < x1 && py < y1;
+        const int pix = valid ? py * g.W + px : 0;
+        // eps >= |a - exact score| for every target of the cell (see file header)
+        const float2 qi = qinfo[pix];
+        const float rt = __int_as_float(cellinfo[4 * cell + 0]), nt = __int_as_float(cellinfo[4 * cell + 1]);
+        const float nmax = __int_as_float(cellinfo[4 * cell + 2]);
+        const float eps = qi.x * nt + qi.y * rt + rt * (nt + rt) + 2.0e-5f * (qi.y * nt + nmax) + 1.0e-5f * nmax;
+        const float eps2 = 2.0f * up(eps);
+        size_t task = 0;
+        if (valid) {
+          const int ci = cell % g.ncellx, cj = cell / g.ncellx;
+          int cimin, cimax, cjmin, cjmax;
+          cell_range(px, g.cellw, g.ncellx, g.R, &cimin, &cimax);
+          cell_range(py, g.cellh, g.ncelly, g.R, &cjmin, &cjmax);
+          task = (size_t)pix * g.nblk + (ci - cimin) * (cjmax - cjmin + 1) + (cj - cjmin);
+        }
+        uint16_t* cand_row = cand + task * kCand;
+
+        float lst[KC];
+#pragma unroll
+        for (int j = 0; j < KC; ++j) lst[j] = CUDART_INF_F;
+        float bound = 0.f;
+        int ns = 0;
+
+        // pass 0: one group = 32 consecutive score columns of this row; the k smallest group minima are k distinct
+        // targets' scores, so the largest of them bounds the k-th smallest score of the cell from above
+        auto track = [&](const uint32_t (&r)[32], int pos0, bool first) {
+          if constexpr (DBG) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              dbg_scores[((size_t)(item * kTilesPerItem + mt) * kTileM + row) * g.Tpad + pos0 + j] = __uint_as_float(r[j]);
+          }
+          if (first) {   // first group of the cell: 16 pair minima (distinct elements) seed the list
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              list_insert<KC>(lst, fminf(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])));
+          } else {
+            float m[11];
+#pragma unroll
+            for (int j = 0; j < 10; ++j)
+              m[j] = fmin3(__uint_as_float(r[3 * j]), __uint_as_float(r[3 * j + 1]), __uint_as_float(r[3 * j + 2]));
+            m[10] = fminf(__uint_as_float(r[30]), __uint_as_float(r[31]));
+            const float gm = fmin3(fmin3(m[0], m[1], m[2]), fmin3(m[3], m[4], m[5]),
+                                   fmin3(fmin3(m[6], m[7], m[8]), m[9], m[10]));
+            list_insert<KC>(lst, gm);
+          }
+        };
+        // pass 1: every score <= the final bound is a candidate for the exact re-rank
+        auto pick = [&](const uint32_t (&r)[32], int pos0) {
+          uint32_t mask = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (__uint_as_float(r[j]) <= bound) mask |= 1u << j;
+          while (mask) {
+            const int j = __ffs((int)mask) - 1;
+            mask &= mask - 1;
+            if (valid && ns < kCand)
+              cand_row[ns] = (uint16_t)(((uint32_t)(pos0 + j) * (uint32_t)g.stride_s) % (uint32_t)g.T);
+            ++ns;
+          }
+        };
+
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+          for (int c = 0; c < nchunks; ++c, ++bcount) {
+            const uint32_t acc = bcount % kAccStages, aph = (bcount / kAccStages) & 1;
+            ptx::mbar_wait_backoff(&ss->t_full[acc], aph, 100);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (acc * kTilesPerItem + mt) * kChunkN;
+            const int cpos = c * kChunkN;
+            if (experiment >= 77) {   // timing experiment: TMA + MMA pipeline only
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(&ss->t_empty[acc]);
+              continue;
+            }
+            uint32_t r0[32], r1[32];
+            ptx::tmem_ld_32x32(taddr, r0);
+            ptx::tmem_ld_wait();
+#pragma unroll 1
+            for (int h = 0; h < kChunkN / 64; ++h) {
+              ptx::tmem_ld_32x32(taddr + 64 * h + 32, r1);      // in flight while r0 is processed
+              if (pass == 0) track(r0, cpos + 64 * h, c == 0 && h == 0);
+              else pick(r0, cpos + 64 * h);
+              ptx::tmem_ld_wait();
+              if (h + 1 < kChunkN / 64) {
+                ptx::tmem_ld_32x32(taddr + 64 * h + 64, r0);
+              } else {
+                ptx::tc_fence_before();                          // all TMEM reads of this stage are done
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&ss->t_empty[acc]);
+              }
+              if (pass == 0) track(r1, cpos + 64 * h + 32, false);
+              else pick(r1, cpos + 64 * h + 32);
+              ptx::tmem_ld_wait();
+            }
+          }
+          bound = lst[KC - 1] + eps2;
+        }
+        int ns_stat = 0;
+        if (valid) {
+          cand_cnt[task] = ns > kCand ? 255 : (uint8_t)ns;
+          if (ns > kCand) atomicAdd(counters + 2, 1);          // diagnostics (rare)
+          else ns_stat = ns;
+        }
+        if (counters_on) {   // diagnostics: one atomic per warp and cell
+          const int tot = __reduce_add_sync(0xffffffffu, ns_stat);
+          if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 4), (unsigned long long)tot);
+        }
+      }
+    } else {
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
     const int mt = (warp - 2) >> 2;              // which of the item's tiles this warp serves
     const int row = quad * 32 + lane;            // query row of the tile = TMEM lane
@@ -468,6 +596,7 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __re
         if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 4), (unsigned long long)tot);
       }
     }
+      }
   }
   ptx::tc_fence_before();
   __syncthreads();
