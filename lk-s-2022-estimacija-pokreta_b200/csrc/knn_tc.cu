@@ -45,18 +45,29 @@ constexpr int kTilesPerItem = 1;                        // MMA tiles (x-adjacent
                                                          // stream but leaves one CTA per SM (measured slower: the
                                                          // selection epilogue, not the stream, bounds the kernel)
 constexpr int kChunkN = 128;       // targets per accumulator stage
-constexpr int kBStages = 2;
-constexpr int kAccStages = 2;
-constexpr int kTmemCols = kAccStages * kTilesPerItem * kChunkN;   // 256: two CTAs per SM
-constexpr int kSlabBytes = kTileM * 32;                  // one k16 block of 128 rows: 4096 B
-constexpr int kTileBytes = kKB * kSlabBytes;             // 20480 B
-constexpr int kListCap = 96;       // per-row candidate list in shared memory (compacted when > kListCap - 8)
 // Two passes over a cell's targets (the GEMM is recomputed; the tensor pipe is mostly idle anyway): pass 0 only
 // tracks the k smallest group minima (tau), pass 1 compares every score with the FINAL bound tau + 2 eps and
 // writes the few survivors straight to the candidate array.  No shared-memory lists, no compaction, ~3.6
 // instead of ~6.5 issue slots per score.  false = the single-pass streaming selection (kept for reference).
 constexpr bool kTwoPass = true;
 constexpr int kPasses = kTwoPass ? 2 : 1;
+#ifndef FLOWB200_KNN_CTAS
+#define FLOWB200_KNN_CTAS 3
+#endif
+#ifndef FLOWB200_KNN_BSTAGES
+#define FLOWB200_KNN_BSTAGES 2
+#endif
+// The two-pass selection needs no shared-memory lists, so more CTAs fit an SM: with ONE accumulator stage (128 TMEM
+// columns) three or four CTAs are resident and it is the other CTAs' epilogues, not a second accumulator stage of the
+// same CTA, that overlap a CTA's MMAs.
+constexpr int kCtasPerSM = kTwoPass ? FLOWB200_KNN_CTAS : 2 / kTilesPerItem;
+constexpr int kBStages = kTwoPass ? FLOWB200_KNN_BSTAGES : 2;
+constexpr int kAccStages = kTwoPass ? 1 : 2;
+constexpr int kTmemCols = kAccStages * kTilesPerItem * kChunkN;   // 128 (256 single-pass: two CTAs per SM)
+constexpr int kSlabBytes = kTileM * 32;                  // one k16 block of 128 rows: 4096 B
+constexpr int kTileBytes = kKB * kSlabBytes;             // 20480 B
+constexpr int kListCap = 96;       // (single-pass selection only) per-row candidate list in shared memory (compacted when > kListCap - 8)
+constexpr int kListBytes = kTwoPass ? 0 : kTilesPerItem * kListCap * kTileM * 4;
 constexpr int kCand = 32;          // candidates handed to the exact re-rank per (query, cell)
 constexpr int kSelThreads = 64 + 128 * kTilesPerItem;     // TMA warp, MMA warp, 4 epilogue warps per tile
 constexpr float kPadNorm = 60000.0f;   // n_hi of padding target rows: their score can never be selected
@@ -233,7 +244,7 @@ __device__ __forceinline__ bool decode_item(const KnnTcGeom& g, int item, int& c
 }
 
 template <int KC, bool DBG>
-__global__ void __launch_bounds__(kSelThreads, 2 / kTilesPerItem)
+__global__ void __launch_bounds__(kSelThreads, kCtasPerSM)
 knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __restrict__ t16, KnnTcGeom g,
                   int n_items, const float2* __restrict__ qinfo, const int* __restrict__ cellinfo,
                   uint16_t* __restrict__ cand, uint8_t* __restrict__ cand_cnt, int32_t* __restrict__ counters,
@@ -243,7 +254,7 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __re
   uint8_t* sA = smem;                                                                     // [tile][5 slabs]
   uint8_t* sB = smem + kTileBytes * kTilesPerItem;                                         // [stage][5 slabs]
   uint32_t* list_e = reinterpret_cast<uint32_t*>(smem + kTileBytes * (kTilesPerItem + kBStages));   // [tile][kListCap][128]
-  SelSmem* ss = reinterpret_cast<SelSmem*>(list_e + kTilesPerItem * kListCap * kTileM);
+  SelSmem* ss = reinterpret_cast<SelSmem*>(reinterpret_cast<uint8_t*>(list_e) + kListBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = g.Tpad / kChunkN;
@@ -941,7 +952,7 @@ static TcLayout tc_layout(const flowb200_params* p) {
   const size_t n = (size_t)g.H * g.W, ncell = (size_t)g.ncellx * g.ncelly;
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off += align_up(b, 1024); return o; };
-  L.grid = (2 / kTilesPerItem) * kNumSMs;
+  L.grid = kCtasPerSM * kNumSMs;
   L.fb_cap = 1 << 20;
   L.q16 = take(n * kKP * 2);
   L.t16 = take(ncell * g.Tpad * kKP * 2);
@@ -992,7 +1003,7 @@ static int run_tc(const float* desc_src, const float* desc_tgt, const flowb200_p
   CUtensorMap mq;
   if (!make_map(&mq, q16, (uint64_t)g.W, (uint64_t)g.H, kTileW, kTileH)) return FLOWB200_ECUDA;
   const int n_items = ncell * g.tiles_x * g.tiles_y;
-  const size_t smem = (size_t)kTileBytes * (kTilesPerItem + kBStages) + (size_t)kTilesPerItem * kListCap * kTileM * 4 +
+  const size_t smem = (size_t)kTileBytes * (kTilesPerItem + kBStages) + (size_t)kListBytes +
                       sizeof(SelSmem) + 1024;
   auto kern = dbg_scores ? knn_select_kernel<KC, true> : knn_select_kernel<KC, false>;
   FB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
