@@ -408,13 +408,15 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __re
         auto pick = [&](const uint32_t (&r)[32], int pos0) {
           uint32_t mask = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (__uint_as_float(r[j]) <= bound) mask |= 1u << j;
+          for (int j = 0; j < 32; ++j) {   // set.le gives all ones / zero: one compare + one logic op per score
+            uint32_t d;
+            asm("set.le.u32.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(r[j])), "f"(bound));
+            mask |= d & (1u << j);
+          }
           while (mask) {
             const int j = __ffs((int)mask) - 1;
             mask &= mask - 1;
-            if (valid && ns < kCand)
-              cand_row[ns] = (uint16_t)(((uint32_t)(pos0 + j) * (uint32_t)g.stride_s) % (uint32_t)g.T);
+            if (valid && ns < kCand) cand_row[ns] = (uint16_t)(pos0 + j);   // position; knn_rerank maps it to the index
             ++ns;
           }
         };
@@ -632,6 +634,12 @@ __device__ __forceinline__ double exact_dist(const float* __restrict__ q, const 
   return acc;
 }
 
+// candidate array entry -> target index inside the cell: the two-pass selection stores the POSITION in the cell's
+// permuted target order (the modulo is cheaper here, one lane per candidate, than in the selection's hit loop)
+__device__ __forceinline__ int cand_index(const KnnTcGeom& g, uint32_t c) {
+  return kTwoPass ? (int)((c * (uint32_t)g.stride_s) % (uint32_t)g.T) : (int)c;
+}
+
 template <int KC>
 __device__ __forceinline__ void emit_proposal(const KnnTcGeom& g, const float* __restrict__ q, const float* __restrict__ desc_tgt,
                                               int qx, int qy, int ci, int cj, int blk, int rank, int idx,
@@ -728,14 +736,14 @@ knn_rerank_kernel(const float* __restrict__ desc_src, const float* __restrict__ 
       const float* tp0 = nullptr;
       const float* tp1 = nullptr;
       if (sub < n) {
-        id0 = cand[task * kCand + sub];
+        id0 = cand_index(g, cand[task * kCand + sub]);
         const int r = id0 / g.cellw, cc = id0 - r * g.cellw;
         tp0 = desc_tgt + ((size_t)(ty0 + r) * g.W + tx0 + cc) * kDescDim;
         screen_and_cost(qp, tp0, ds0, co0);
       }
       const bool two = n > 16;
       if (two && 16 + sub < n) {
-        id1 = cand[task * kCand + 16 + sub];
+        id1 = cand_index(g, cand[task * kCand + 16 + sub]);
         const int r = id1 / g.cellw, cc = id1 - r * g.cellw;
         tp1 = desc_tgt + ((size_t)(ty0 + r) * g.W + tx0 + cc) * kDescDim;
         screen_and_cost(qp, tp1, ds1, co1);
