@@ -138,6 +138,19 @@ int flowb200_bcd(const int32_t* pvec, const void* cost, const int32_t* nprop, in
                  int H, int W, int K, int bcd_mode, double lamda, int tpsi, int cost_shift, int sweeps,
                  int32_t* labels_per_sweep, void* workspace, size_t workspace_bytes, flowb200_stream_t stream);
 
+/* The int32 programme in pieces, for a caller that splits the (independent) chains of every phase over several
+ * GPUs and exchanges the labels between phases (single-huge-image mode): part `part` of `nparts` owns
+ * a contiguous range of every phase's chains.  flowb200_bcd_prepare compiles the K-sets of the owned chains (once per
+ * proposal set); flowb200_bcd_phase runs the owned chains of one phase (0 even columns down, 1 even rows right to
+ * left, 2 odd columns up, 3 odd rows left to right; python bcd.py:265-277) in place on labels.
+ * flowb200_bcd(sweeps) == prepare(0,1) + sweeps x phases 0..3 (0,1).  INT32 / INT32_F32COST modes only. */
+int flowb200_bcd_prepare(const int32_t* pvec, const void* cost, const int32_t* nprop, int H, int W, int K,
+                         int bcd_mode, double lamda, int tpsi, int cost_shift, int part, int nparts,
+                         void* workspace, size_t workspace_bytes, flowb200_stream_t stream);
+int flowb200_bcd_phase(const int32_t* pvec, const void* cost, const int32_t* nprop, int32_t* labels, int H, int W,
+                       int K, int bcd_mode, double lamda, int tpsi, int cost_shift, int phase, int part, int nparts,
+                       void* workspace, size_t workspace_bytes, flowb200_stream_t stream);
+
 /* ---- A5  vratiKonacniFlow (daisy i flann.py:192-197) + A12 FlowImage.ucitajFlow (postprocessing.py:7-17) ----
  * flow_yx (optional): float64 [H][W][2] = (dy,dx);  uvv (optional): float32 [H][W][3] = (dx, dy, 1). */
 int flowb200_flow_from_labels(const int32_t* pvec, const int32_t* labels, int H, int W, int K,

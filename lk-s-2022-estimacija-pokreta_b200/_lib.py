@@ -49,6 +49,10 @@ SYMBOLS = {
     "flowb200_bcd_min_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "flowb200_bcd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                C.c_int, _P, _P, C.c_size_t, _P]),
+    "flowb200_bcd_prepare": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, _P, C.c_size_t, _P]),
+    "flowb200_bcd_phase": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "flowb200_flow_from_labels": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "flowb200_consistency": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "flowb200_epe": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P]),

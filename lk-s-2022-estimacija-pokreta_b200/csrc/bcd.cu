@@ -665,6 +665,37 @@ extern "C" int flowb200_bcd(const int32_t* pvec, const void* cost, const int32_t
   }
 }
 
+// ---- the K-set programme in pieces: one part of every phase's chains (single-huge-image mode) ----
+extern "C" int flowb200_bcd_prepare(const int32_t* pvec, const void* cost, const int32_t* nprop, int H, int W, int K,
+                                    int bcd_mode, double lamda, int tpsi, int cost_shift, int part, int nparts,
+                                    void* workspace, size_t workspace_bytes, flowb200_stream_t stream) {
+  if (!pvec || !cost || !nprop || !workspace) return FLOWB200_EINVAL;
+  if (H <= 0 || W <= 0 || K <= 0 || K > 512 || H > 16384 || W > 16384) return FLOWB200_EINVAL;
+  if (cost_shift < 0 || cost_shift > 14) return FLOWB200_EINVAL;
+  if (bcd_mode == FLOWB200_BCD_INT32)
+    return ksets_prepare<int32_t>(pvec, static_cast<const int32_t*>(cost), nprop, H, W, K, lamda, tpsi, cost_shift, part,
+                                  nparts, workspace, workspace_bytes, stream);
+  if (bcd_mode == FLOWB200_BCD_INT32_F32COST)
+    return ksets_prepare<float>(pvec, static_cast<const float*>(cost), nprop, H, W, K, lamda, tpsi, cost_shift, part,
+                                nparts, workspace, workspace_bytes, stream);
+  return FLOWB200_EUNSUPPORTED;
+}
+
+extern "C" int flowb200_bcd_phase(const int32_t* pvec, const void* cost, const int32_t* nprop, int32_t* labels, int H,
+                                  int W, int K, int bcd_mode, double lamda, int tpsi, int cost_shift, int phase, int part,
+                                  int nparts, void* workspace, size_t workspace_bytes, flowb200_stream_t stream) {
+  if (!pvec || !cost || !nprop || !labels || !workspace) return FLOWB200_EINVAL;
+  if (H <= 0 || W <= 0 || K <= 0 || K > 512 || H > 16384 || W > 16384) return FLOWB200_EINVAL;
+  if (cost_shift < 0 || cost_shift > 14) return FLOWB200_EINVAL;
+  if (bcd_mode == FLOWB200_BCD_INT32)
+    return ksets_phase<int32_t>(pvec, static_cast<const int32_t*>(cost), nprop, labels, H, W, K, lamda, tpsi, cost_shift,
+                                phase, part, nparts, workspace, workspace_bytes, stream);
+  if (bcd_mode == FLOWB200_BCD_INT32_F32COST)
+    return ksets_phase<float>(pvec, static_cast<const float*>(cost), nprop, labels, H, W, K, lamda, tpsi, cost_shift,
+                              phase, part, nparts, workspace, workspace_bytes, stream);
+  return FLOWB200_EUNSUPPORTED;
+}
+
 extern "C" int flowb200_quantise_costs(const float* lcost, int32_t* m, size_t n, double lamda, int shift,
                                        flowb200_stream_t stream) {
   if (!lcost || !m || shift < 0 || shift > 14) return FLOWB200_EINVAL;

@@ -47,6 +47,16 @@ template <typename CostT>
 int launch_sweeps_ksets(const int32_t* pvec, const CostT* cost, const int32_t* nprop, int32_t* labels, int H, int W,
                         int K, double lamda, int tpsi, int shift, int sweeps, int32_t* labels_per_sweep,
                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
+// the same in pieces, for callers that exchange labels between phases (single-huge-image mode): part `part` of `nparts`
+// owns a contiguous range of every phase's chains
+template <typename CostT>
+int ksets_prepare(const int32_t* pvec, const CostT* cost, const int32_t* nprop, int H, int W, int K, double lamda,
+                  int tpsi, int shift, int part, int nparts, void* workspace, size_t workspace_bytes,
+                  cudaStream_t stream);
+template <typename CostT>
+int ksets_phase(const int32_t* pvec, const CostT* cost, const int32_t* nprop, int32_t* labels, int H, int W, int K,
+                double lamda, int tpsi, int shift, int phase, int part, int nparts, void* workspace,
+                size_t workspace_bytes, cudaStream_t stream);
 size_t ksets_workspace_bytes(int H, int W, int K);
 size_t ksets_min_workspace_bytes(int H, int W, int K);   // fixed part only: every K-set is then evaluated densely
 

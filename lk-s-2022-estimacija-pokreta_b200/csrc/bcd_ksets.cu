@@ -165,7 +165,8 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
                   const uint16_t* __restrict__ sorig, const int32_t* __restrict__ svec, int H, int W, int K, int Kst,
                   int Kpad, int tpsi, int bshift, int shift, double lamda, uint32_t slot_bytes,
                   unsigned char* __restrict__ arena, unsigned long long arena_bytes,
-                  unsigned long long* __restrict__ cursor, unsigned long long* __restrict__ desc) {
+                  unsigned long long* __restrict__ cursor, unsigned long long* __restrict__ desc, int part,
+                  int nparts) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int t = threadIdx.x, lane = t & 31;
   uint32_t* rng = reinterpret_cast<uint32_t*>(smem_raw);
@@ -193,6 +194,15 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
     const int orient = task >= npix ? 1 : 0;
     const int p = task - orient * npix;
     const int y = p / W, x = p - y * W;
+    if (nparts > 1) {   // only the records of the chains this part runs (column x: chain x/2 of phase 0 or 2; row y alike)
+      const int line = orient ? y : x;
+      const long long nch = orient ? ((line & 1) ? H / 2 : (H + 1) / 2) : ((line & 1) ? W / 2 : (W + 1) / 2);
+      const int c = line >> 1;
+      if (c < (int)(nch * part / nparts) || c >= (int)(nch * (part + 1) / nparts)) {
+        if (t == 0) desc[task] = 0ull;
+        continue;
+      }
+    }
     const int q = prev_pixel(y, x, orient, H, W);
     const int n = nprop[p];
     const int nq = q >= 0 ? nprop[q] : 0;
@@ -413,7 +423,7 @@ struct ChainArgs {
   uint16_t* bp;
   const unsigned long long* desc;
   const unsigned char* arena;
-  int H, W, K, Kpad, phase, tpsi, shift, slot_shift;   // 1 << slot_shift slots
+  int H, W, K, Kpad, phase, chain0, tpsi, shift, slot_shift;   // chain = chain0 + blockIdx.x; 1 << slot_shift slots
   uint32_t slot_bytes;
   double lamda;
 };
@@ -428,7 +438,7 @@ __host__ __device__ inline size_t chain_fixed_smem(int Kpad, int len) {
 template <typename CostT, int T>
 __device__ __forceinline__ void chain_body(const ChainArgs& a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const ChainGeom g = chain_geom(a.phase, blockIdx.x, a.H, a.W);
+  const ChainGeom g = chain_geom(a.phase, a.chain0 + (int)blockIdx.x, a.H, a.W);
   const int t = threadIdx.x, lane = t & 31, wfirst = t & ~31;
   const int K = a.K, Kpad = a.Kpad, shift = a.shift, tpsi = a.tpsi;
   const int S = 1 << a.slot_shift, smask = S - 1;
@@ -664,64 +674,101 @@ KsetLayout kset_layout(int H, int W, int K, size_t workspace_bytes) {
 size_t ksets_workspace_bytes(int H, int W, int K) { return kset_layout(H, W, K, 0).total; }
 size_t ksets_min_workspace_bytes(int H, int W, int K) { return kset_layout(H, W, K, 0).arena; }
 
+// chains [c0, c1) of `phase` that part `part` of `nparts` owns (single-huge-image mode: a phase's independent chains
+// are split over the GPUs, python bcd.py:265-277 makes every chain of a phase independent of the others)
+static inline void owned_chains(int phase, int H, int W, int part, int nparts, int* c0, int* c1) {
+  const long long n = phase_chains(phase, H, W);
+  *c0 = (int)(n * part / nparts);
+  *c1 = (int)(n * (part + 1) / nparts);
+}
+
 template <typename CostT>
-int launch_sweeps_ksets(const int32_t* pvec, const CostT* cost, const int32_t* nprop, int32_t* labels, int H, int W,
-                        int K, double lamda, int tpsi, int shift, int sweeps, int32_t* labels_per_sweep,
-                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+struct KsetPlan {
+  KsetLayout L;
+  void (*kern)(const ChainArgs) = nullptr;
+  int T = 0, bshift = 0, slot_shift = 2;
+  uint32_t slot_bytes = 0;
+  size_t smem = 0;
+};
+
+template <typename CostT>
+static int make_plan(int H, int W, int K, int tpsi, int shift, size_t workspace_bytes, KsetPlan<CostT>* P) {
   if (K > 512 || tpsi < 1 || tpsi > 8) return FLOWB200_EUNSUPPORTED;
   {   // dp is a uint32
     const unsigned long long per_step = ((unsigned long long)(3 * tpsi) << shift) + 65535ull;
     if ((unsigned long long)(H > W ? H : W) * per_step >= 0xFFFF0000ull) return FLOWB200_EUNSUPPORTED;
   }
-  const KsetLayout L = kset_layout(H, W, K, workspace_bytes);
-  if (workspace_bytes < L.arena) return FLOWB200_EWORKSPACE;
-  char* ws = static_cast<char*>(workspace);
-  const int Kpad = L.Kpad;
-  const int npix = H * W;
-  int bshift = 0;
-  while ((1 << bshift) < tpsi) ++bshift;
-
-  void (*kern)(const ChainArgs) = nullptr;
-  int T = 0, minb = 1;
-#define FB_KS_CASE(TT, MB) if (!kern && K <= TT) { kern = kset_chain_kernel<CostT, TT, MB>; T = TT; minb = MB; }
+  P->L = kset_layout(H, W, K, workspace_bytes);
+  if (workspace_bytes < P->L.arena) return FLOWB200_EWORKSPACE;
+  const int Kpad = P->L.Kpad;
+  while ((1 << P->bshift) < tpsi) ++P->bshift;
+  int minb = 1;
+#define FB_KS_CASE(TT, MB) if (!P->kern && K <= TT) { P->kern = kset_chain_kernel<CostT, TT, MB>; P->T = TT; minb = MB; }
   FB_KS_CASE(64, 8) FB_KS_CASE(128, 6) FB_KS_CASE(192, 5) FB_KS_CASE(256, 4) FB_KS_CASE(320, 4)
   FB_KS_CASE(384, 3) FB_KS_CASE(512, 2)
 #undef FB_KS_CASE
-  if (!kern) return FLOWB200_EUNSUPPORTED;
-
+  if (!P->kern) return FLOWB200_EUNSUPPORTED;
   // ring of record slots: as many (<= 4) as keep `minb` chains per SM resident
   const int maxlen = H > W ? H : W;
   // (masked lanes of the entry loop may also read up to 8272 bytes past the start of shared memory)
   const size_t fixed = std::max(chain_fixed_smem(Kpad, maxlen) + kSlotSlack, (size_t)8448);
   // a slot holds the largest record the build kernel can stage: header, round offsets, n structs, staged entries
-  uint32_t slot_bytes =
+  P->slot_bytes =
       (uint32_t)((kRecHeader + 288 + 8 * (size_t)Kpad + 2 * (size_t)kStagePerLabel * Kpad + 127) & ~(size_t)127);
-  int slot_shift = 2;
   const size_t budget = (size_t)(227 * 1024) / minb - 1024;
-  if (fixed + 4 * (size_t)slot_bytes > budget) slot_shift = 1;
+  if (fixed + 4 * (size_t)P->slot_bytes > budget) P->slot_shift = 1;
   // long chains (large images): fewer resident chains rather than smaller slots
-  if (fixed + ((size_t)slot_bytes << slot_shift) > (size_t)227 * 1024) return FLOWB200_EUNSUPPORTED;
-  const size_t smem = fixed + ((size_t)slot_bytes << slot_shift);
-  FB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (fixed + ((size_t)P->slot_bytes << P->slot_shift) > (size_t)227 * 1024) return FLOWB200_EUNSUPPORTED;
+  P->smem = fixed + ((size_t)P->slot_bytes << P->slot_shift);
+  FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem));
+  return FLOWB200_OK;
+}
 
-  if (sweeps > 0) {
-    uint16_t* sorig = reinterpret_cast<uint16_t*>(ws + L.sorig);
-    unsigned long long* cursor = reinterpret_cast<unsigned long long*>(ws + L.cursor);
-    FB_CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), stream));
-    int32_t* svec = reinterpret_cast<int32_t*>(ws + L.svec);
-    kset_sort_kernel<<<min((npix + kSortWarps - 1) / kSortWarps, 8 * kNumSMs), kSortWarps * 32, 0, stream>>>(
-        pvec, nprop, npix, K, L.Kst, bshift, sorig, svec);
-    FB_LAUNCH_CHECK();
-    const size_t bsmem = build_smem_bytes(Kpad);
-    auto bk = kset_build_kernel<CostT>;
-    FB_CUDA_CHECK(cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
-    const int bctas = std::min(16, (int)(227 * 1024 / (bsmem + 1024)));
-    bk<<<min(2 * npix, max(1, bctas) * kNumSMs), kBuildThreads, bsmem, stream>>>(
-        pvec, cost, nprop, sorig, svec, H, W, K, L.Kst, Kpad, tpsi, bshift, shift, lamda, slot_bytes,
-        reinterpret_cast<unsigned char*>(ws + L.arena), (unsigned long long)L.arena_bytes, cursor,
-        reinterpret_cast<unsigned long long*>(ws + L.desc));
-    FB_LAUNCH_CHECK();
-  }
+// sort + record build for the chains this part owns
+template <typename CostT>
+int ksets_prepare(const int32_t* pvec, const CostT* cost, const int32_t* nprop, int H, int W, int K, double lamda,
+                  int tpsi, int shift, int part, int nparts, void* workspace, size_t workspace_bytes,
+                  cudaStream_t stream) {
+  if (nparts < 1 || part < 0 || part >= nparts) return FLOWB200_EINVAL;
+  KsetPlan<CostT> P;
+  const int rc = make_plan<CostT>(H, W, K, tpsi, shift, workspace_bytes, &P);
+  if (rc) return rc;
+  const KsetLayout& L = P.L;
+  char* ws = static_cast<char*>(workspace);
+  const int npix = H * W;
+  uint16_t* sorig = reinterpret_cast<uint16_t*>(ws + L.sorig);
+  unsigned long long* cursor = reinterpret_cast<unsigned long long*>(ws + L.cursor);
+  FB_CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), stream));
+  int32_t* svec = reinterpret_cast<int32_t*>(ws + L.svec);
+  kset_sort_kernel<<<min((npix + kSortWarps - 1) / kSortWarps, 8 * kNumSMs), kSortWarps * 32, 0, stream>>>(
+      pvec, nprop, npix, K, L.Kst, P.bshift, sorig, svec);
+  FB_LAUNCH_CHECK();
+  const size_t bsmem = build_smem_bytes(L.Kpad);
+  auto bk = kset_build_kernel<CostT>;
+  FB_CUDA_CHECK(cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+  const int bctas = std::min(16, (int)(227 * 1024 / (bsmem + 1024)));
+  bk<<<min(2 * npix, max(1, bctas) * kNumSMs), kBuildThreads, bsmem, stream>>>(
+      pvec, cost, nprop, sorig, svec, H, W, K, L.Kst, L.Kpad, tpsi, P.bshift, shift, lamda, P.slot_bytes,
+      reinterpret_cast<unsigned char*>(ws + L.arena), (unsigned long long)L.arena_bytes, cursor,
+      reinterpret_cast<unsigned long long*>(ws + L.desc), part, nparts);
+  FB_LAUNCH_CHECK();
+  return FLOWB200_OK;
+}
+
+// one phase, the chains this part owns, in place on labels
+template <typename CostT>
+int ksets_phase(const int32_t* pvec, const CostT* cost, const int32_t* nprop, int32_t* labels, int H, int W, int K,
+                double lamda, int tpsi, int shift, int phase, int part, int nparts, void* workspace,
+                size_t workspace_bytes, cudaStream_t stream) {
+  if (nparts < 1 || part < 0 || part >= nparts || phase < 0 || phase > 3) return FLOWB200_EINVAL;
+  KsetPlan<CostT> P;
+  const int rc = make_plan<CostT>(H, W, K, tpsi, shift, workspace_bytes, &P);
+  if (rc) return rc;
+  const KsetLayout& L = P.L;
+  char* ws = static_cast<char*>(workspace);
+  int c0, c1;
+  owned_chains(phase, H, W, part, nparts, &c0, &c1);
+  if (c1 <= c0) return FLOWB200_OK;
   ChainArgs a{};
   a.pvec = pvec;
   a.cost = cost;
@@ -730,16 +777,31 @@ int launch_sweeps_ksets(const int32_t* pvec, const CostT* cost, const int32_t* n
   a.bp = reinterpret_cast<uint16_t*>(ws + L.bp);
   a.desc = reinterpret_cast<const unsigned long long*>(ws + L.desc);
   a.arena = reinterpret_cast<const unsigned char*>(ws + L.arena);
-  a.H = H; a.W = W; a.K = K; a.Kpad = Kpad; a.tpsi = tpsi; a.shift = shift; a.slot_shift = slot_shift;
-  a.slot_bytes = slot_bytes;
+  a.H = H; a.W = W; a.K = K; a.Kpad = L.Kpad; a.tpsi = tpsi; a.shift = shift; a.slot_shift = P.slot_shift;
+  a.slot_bytes = P.slot_bytes;
   a.lamda = lamda;
+  a.phase = phase;
+  a.chain0 = c0;
+  P.kern<<<c1 - c0, P.T, P.smem, stream>>>(a);
+  FB_LAUNCH_CHECK();
+  return FLOWB200_OK;
+}
+
+template <typename CostT>
+int launch_sweeps_ksets(const int32_t* pvec, const CostT* cost, const int32_t* nprop, int32_t* labels, int H, int W,
+                        int K, double lamda, int tpsi, int shift, int sweeps, int32_t* labels_per_sweep,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (sweeps <= 0) {
+    KsetPlan<CostT> P;
+    return make_plan<CostT>(H, W, K, tpsi, shift, workspace_bytes, &P);
+  }
+  int rc = ksets_prepare<CostT>(pvec, cost, nprop, H, W, K, lamda, tpsi, shift, 0, 1, workspace, workspace_bytes, stream);
+  if (rc) return rc;
   for (int w = 0; w < sweeps; ++w) {
     for (int phase = 0; phase < 4; ++phase) {
-      const int nch = phase_chains(phase, H, W);
-      if (nch == 0) continue;
-      a.phase = phase;
-      kern<<<nch, T, smem, stream>>>(a);
-      FB_LAUNCH_CHECK();
+      rc = ksets_phase<CostT>(pvec, cost, nprop, labels, H, W, K, lamda, tpsi, shift, phase, 0, 1, workspace,
+                              workspace_bytes, stream);
+      if (rc) return rc;
     }
     if (labels_per_sweep)
       FB_CUDA_CHECK(cudaMemcpyAsync(labels_per_sweep + (size_t)w * H * W, labels, sizeof(int32_t) * H * W,
@@ -748,9 +810,15 @@ int launch_sweeps_ksets(const int32_t* pvec, const CostT* cost, const int32_t* n
   return FLOWB200_OK;
 }
 
-template int launch_sweeps_ksets<int32_t>(const int32_t*, const int32_t*, const int32_t*, int32_t*, int, int, int, double,
-                                          int, int, int, int32_t*, void*, size_t, cudaStream_t);
-template int launch_sweeps_ksets<float>(const int32_t*, const float*, const int32_t*, int32_t*, int, int, int, double, int,
-                                        int, int, int32_t*, void*, size_t, cudaStream_t);
+#define FB_KS_INSTANTIATE(CT)                                                                                          \
+  template int launch_sweeps_ksets<CT>(const int32_t*, const CT*, const int32_t*, int32_t*, int, int, int, double, int, \
+                                       int, int, int32_t*, void*, size_t, cudaStream_t);                               \
+  template int ksets_prepare<CT>(const int32_t*, const CT*, const int32_t*, int, int, int, double, int, int, int, int,  \
+                                 void*, size_t, cudaStream_t);                                                         \
+  template int ksets_phase<CT>(const int32_t*, const CT*, const int32_t*, int32_t*, int, int, int, double, int, int,    \
+                               int, int, int, void*, size_t, cudaStream_t);
+FB_KS_INSTANTIATE(int32_t)
+FB_KS_INSTANTIATE(float)
+#undef FB_KS_INSTANTIATE
 
 }  // namespace flowb200

@@ -6,10 +6,10 @@ its band and the source descriptors to the columns whose +-cell_radius window re
 ordinary per-cell exact search on that sub-image).  In the reference's slot order (daisy i flann.py:162-177: cell
 column major, cell row minor, then rank) the proposals one source pixel gets from one band are ONE contiguous slot
 range, so the "merge of per-GPU top-K lists" is not a comparison merge: every rank broadcasts its block and every
-rank copies slot ranges into place (`merge_bands`, NCCL over NVLink; gloo in the CPU tests).  Everything after the
-merge (random proposals, BCD, consistency) runs replicated on the merged proposal set, with identical results on
-every rank; splitting the BCD chains of a phase across ranks with a label all-gather per phase is the next step and
-not built yet.
+rank copies slot ranges into place (`merge_bands`, NCCL over NVLink; gloo in the CPU tests).  BCD shards too: the
+chains of a phase are independent, every rank runs a contiguous share of them and one all-reduce of the label
+differences per phase gives every rank the phase's result (`bcd_sharded`).  DAISY, the random proposals and the
+consistency check are cheap and run replicated, with identical results on every rank.
 
 All functions here are host-side planning and torch.distributed plumbing; the arithmetic is the C-ABI kernels'.
 """
@@ -161,6 +161,28 @@ def knn_proposals_sharded(desc_src, desc_tgt, p: FlowParams, rank, world, dist=N
     return merge_bands(p, bands, rank, sub_pvec, sub_lcost, desc_src.device, dist)
 
 
+def bcd_sharded(pvec, cost, nprop, labels, sweeps, p: FlowParams, mode, rank, world, dist=None):
+    """ceoBCD with every phase's chains split over the ranks.  The chains of a phase are independent (they read and
+    write only their own pixels), so a rank runs its share and the ranks then exchange what changed: every rank holds
+    the full label image, `new - old` is zero outside the rank's own chains, and one all-reduce(sum) of that difference
+    per phase (4 bytes per pixel over NVLink) gives every rank the phase's result."""
+    from . import ops
+    ws = ops.bcd_workspace(pvec)
+    kw = dict(mode=mode, lamda=p.lamda, tpsi=p.tpsi, cost_shift=p.cost_shift)
+    ops.bcd_prepare(pvec, cost, nprop, ws, rank, world, **kw)
+    for _ in range(sweeps):
+        for phase in range(4):
+            if dist is None or world == 1:
+                ops.bcd_phase(pvec, cost, nprop, labels, ws, phase, rank, world, **kw)
+                continue
+            before = labels.clone()
+            ops.bcd_phase(pvec, cost, nprop, labels, ws, phase, rank, world, **kw)
+            delta = labels - before
+            dist.all_reduce(delta)
+            labels.copy_(before + delta)
+    return labels
+
+
 def flow_pair_sharded(bgr0, bgr1, p: FlowParams, sweeps, directions, seed, bcd_mode, rank, world, dist=None,
                       want_raw=False):
     """The whole path for ONE pair on `world` ranks: DAISY replicated, proposal search sharded by target cell band and
@@ -173,8 +195,11 @@ def flow_pair_sharded(bgr0, bgr1, p: FlowParams, sweeps, directions, seed, bcd_m
         src, tgt = d[direction], d[1 - direction]
         pvec, lcost, nprop, labels = knn_proposals_sharded(src, tgt, p, rank, world, dist)
         ops.random_proposals(src, tgt, p, pvec, lcost, nprop, labels, seed=seed + direction)
-        mode = _lib.BCD_INT32_F32COST if bcd_mode in (_lib.BCD_INT32, _lib.BCD_INT32_F32COST) else _lib.BCD_FP64_F32COST
-        ops.bcd(pvec, lcost, nprop, labels, sweeps, mode=mode, lamda=p.lamda, tpsi=p.tpsi, cost_shift=p.cost_shift)
+        if bcd_mode in (_lib.BCD_INT32, _lib.BCD_INT32_F32COST):
+            bcd_sharded(pvec, lcost, nprop, labels, sweeps, p, _lib.BCD_INT32_F32COST, rank, world, dist)
+        else:   # the float64 programme is not split: replicated
+            ops.bcd(pvec, lcost, nprop, labels, sweeps, mode=_lib.BCD_FP64_F32COST, lamda=p.lamda, tpsi=p.tpsi,
+                    cost_shift=p.cost_shift)
         uvv.append(ops.flow_from_labels(pvec, labels, want_yx=False)[1])
         del pvec, lcost
     out = uvv[0].clone()

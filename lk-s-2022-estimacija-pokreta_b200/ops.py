@@ -141,6 +141,33 @@ def bcd(pvec, cost, nprop, labels, sweeps, mode=_lib.BCD_FP64_F32COST, lamda=0.0
     return snaps
 
 
+def bcd_workspace(pvec):
+    lib = _lib.load()
+    H, W, K = pvec.shape
+    return _workspace(lib.flowb200_bcd_workspace_bytes(H, W, K), pvec.device)
+
+
+def bcd_prepare(pvec, cost, nprop, ws, part=0, nparts=1, mode=_lib.BCD_INT32_F32COST, lamda=0.05, tpsi=8, cost_shift=12):
+    """Compile the K-sets of the chains part `part` of `nparts` owns into the workspace `ws` (int32 modes)."""
+    lib = _lib.load()
+    H, W, K = pvec.shape
+    _lib.check(lib.flowb200_bcd_prepare(_ptr(pvec, torch.int32, "pvec"), _ptr(cost, _BCD_COST_DTYPE[mode], "cost"),
+                                        _ptr(nprop, torch.int32, "nprop"), H, W, K, int(mode), float(lamda), int(tpsi),
+                                        int(cost_shift), int(part), int(nparts), _ptr(ws), ws.numel(), _stream()),
+               "flowb200_bcd_prepare")
+
+
+def bcd_phase(pvec, cost, nprop, labels, ws, phase, part=0, nparts=1, mode=_lib.BCD_INT32_F32COST, lamda=0.05, tpsi=8,
+              cost_shift=12):
+    """Run the owned chains of one phase in place on labels (after bcd_prepare with the same workspace and part)."""
+    lib = _lib.load()
+    H, W, K = pvec.shape
+    _lib.check(lib.flowb200_bcd_phase(_ptr(pvec, torch.int32, "pvec"), _ptr(cost, _BCD_COST_DTYPE[mode], "cost"),
+                                      _ptr(nprop, torch.int32, "nprop"), _ptr(labels, torch.int32, "labels"), H, W, K,
+                                      int(mode), float(lamda), int(tpsi), int(cost_shift), int(phase), int(part),
+                                      int(nparts), _ptr(ws), ws.numel(), _stream()), "flowb200_bcd_phase")
+
+
 def flow_from_labels(pvec, labels, want_yx=True, want_uvv=True):
     """vratiKonacniFlow (+ FlowImage layout).  Returns (flow_yx float64 (H,W,2) | None, uvv float32 (H,W,3) | None)."""
     lib = _lib.load()

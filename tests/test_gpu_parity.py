@@ -426,3 +426,29 @@ def test_two_ranks_nccl_flow_pair_equals_one_gpu(tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     assert open(tmp_path / "ok0").read() == "True" and open(tmp_path / "ok1").read() == "True"
+
+
+@pytest.mark.parametrize("nparts", [2, 3])
+def test_bcd_in_pieces_equals_whole(nparts):
+    """flowb200_bcd_prepare / flowb200_bcd_phase with the chains of every phase split into parts, the parts run one
+    after the other on this GPU with their own workspaces and label replicas, differences summed as the all-reduce of
+    huge.bcd_sharded does: the reference's labels (bcd_q12 fixture)."""
+    ops, ioc, lib = pkg("ops"), pkg("io_contract"), pkg("_lib")
+    z = load_npz("bcd_q12")
+    sweeps, shift = int(z["meta"][5]), int(z["meta"][6])
+    pvec = dev(ioc.pack_proposals(z["proposals"]))
+    m, nprop = dev(z["m"], torch.int32), dev(z["nprop"], torch.int32)
+    kw = dict(mode=lib.BCD_INT32, cost_shift=shift)
+    wss = [ops.bcd_workspace(pvec).clone() for _ in range(nparts)]
+    for r in range(nparts):
+        ops.bcd_prepare(pvec, m, nprop, wss[r], r, nparts, **kw)
+    labels = dev(z["labels00"], torch.int32)
+    for w in range(sweeps):
+        for phase in range(4):
+            total = torch.zeros_like(labels)
+            for r in range(nparts):
+                mine = labels.clone()
+                ops.bcd_phase(pvec, m, nprop, mine, wss[r], phase, r, nparts, **kw)
+                total += mine - labels
+            labels = labels + total
+        assert np.array_equal(labels.cpu().numpy(), z[f"labels{w + 1:02d}"]), w

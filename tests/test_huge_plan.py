@@ -87,3 +87,36 @@ def test_two_gloo_ranks_exchange_bands(tmp_path):
                        capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert r.returncode == 0, r.stderr[-3000:]
     assert open(tmp_path / "ok0").read() == "True" and open(tmp_path / "ok1").read() == "True"
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_bcd_phases_with_delta_exchange_equal_full_sweeps(world):
+    """Splitting every phase's chains over `world` parts and summing the label differences (what huge.bcd_sharded
+    does with an all-reduce) reproduces the oracle's full sweeps: the chains of a phase are independent."""
+    from oracle import bcd as obcd
+    rng = np.random.default_rng(world)
+    H, W, K = 9, 11, 12
+    prop = rng.integers(-6, 7, (H, W, K, 2)).astype(np.int64)
+    nprop = rng.integers(3, K + 1, (H, W)).astype(np.int64)
+    lc = 20.0 * rng.integers(0, 513, (H, W, K)) / 4096.0
+    lab0 = (rng.integers(0, 1 << 20, (H, W)) % nprop).astype(np.int64)
+    want = obcd.ceo_bcd(prop, lc, nprop, lab0, 2)[-1]
+    phases = [(1, 0, [(0, x) for x in range(0, W, 2)]), (0, -1, [(y, W - 1) for y in range(0, H, 2)]),
+              (-1, 0, [(H - 1, x) for x in range(1, W, 2)]), (0, 1, [(y, 0) for y in range(1, H, 2)])]
+    labels = [lab0.copy() for _ in range(world)]          # every rank's replica
+    for _ in range(2):
+        for ys, xs, starts in phases:
+            n = len(starts)
+            deltas = []
+            for r in range(world):
+                mine = starts[n * r // world:n * (r + 1) // world]
+                before = labels[r].copy()
+                if mine:
+                    obcd._phase(prop, lc, nprop, labels[r], 8, 0.05, ys, xs, mine)
+                deltas.append(labels[r] - before)
+                labels[r] = before
+            total = sum(deltas)                           # the all-reduce
+            for r in range(world):
+                labels[r] = labels[r] + total
+    for r in range(world):
+        assert np.array_equal(labels[r], want)
