@@ -298,7 +298,7 @@ def run_huge(args):
                 "pairs_per_s": 1e3 / ms_step,
                 "config": {"workload": args.workload, "H": p.H, "W": p.W, "K": p.maxnprop, "k_cell": p.k_cell,
                            "n_gauss": p.n_gauss, "bcd_times": sweeps, "directions": directions,
-                           "parallelism": f"1 pair, target cell columns sharded x{world}, broadcast merge; rest replicated",
+                           "parallelism": f"1 pair on {world} rank(s): proposal search sharded by target cell columns (broadcast + slot-range merge), BCD chains of every phase split (all-reduce of label differences); DAISY, random proposals, check replicated",
                            "l2": "working set (GBs of proposals) exceeds L2"},
                 "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * p.H * p.W * 3,
                         "d2h_bytes_per_step": p.H * p.W * 12},
