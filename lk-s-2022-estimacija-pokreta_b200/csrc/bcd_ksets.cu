@@ -2,25 +2,26 @@
 // it evaluates the K-sets S_l = {k : L1(v_l, u_k) < tpsi} ONCE per proposal set (pakovanje, daisy i flann.py:256-309,
 // the 2.6 GB packedksets cache) and only reads them inside bcd() (python bcd.py:131-142).  Here the cache is sparse:
 //
-//   kset_sort_kernel   per pixel: label indices ordered by the spatial-hash bucket of their flow vector
-//   kset_build_kernel  per (pixel, chain orientation): one RECORD = everything a chain step needs, contiguous:
-//                        16 B header | n x {vector, data cost | label, list offset | length} | uint16 entries
-//                      an entry = previous-pixel label k | L1(v_l, u_k) << 10, only pairs with L1 < tpsi.
-//                      Records are carved from an arena with one atomic cursor; a 64-bit descriptor per record
-//                      (offset | size) is the only index.  All (pixel, orientation) pairs are independent, so this
-//                      kernel is throughput bound, unlike the chains.
-//   kset_chain_kernel  one CTA per chain, one thread per label.  Thread 0 streams the chain's records into a ring
-//                      of shared-memory slots with bulk asynchronous copies (TMA engine, mbarrier completion) a few
-//                      steps ahead; a step is: wait for the slot, min over the label's entry list of
-//                      rep[k] + (L1 << ..), add the unary term, publish the new key, one block barrier.
+//   kset_sort_kernel   per pixel: label indices (and vectors) ordered by the spatial-hash bucket of the flow vector
+//   kset_build_kernel  per (pixel, chain orientation): one RECORD = everything a chain step needs, contiguous (layout
+//                      at the kernel).  Only pairs with L1 < tpsi are stored, as uint16 entries (k << 4 | L1 << 13),
+//                      labels ordered by decreasing list length and entries in jagged-diagonal order.  Records are
+//                      carved from an arena with one atomic cursor; a 64-bit descriptor per record (offset | size)
+//                      is the only index.  All (pixel, orientation) pairs are independent, so this kernel is
+//                      throughput bound, unlike the chains.
+//   kset_chain_kernel  one CTA per chain, one thread per label position.  Thread 0 streams the chain's records into a
+//                      ring of shared-memory slots with bulk asynchronous copies (TMA engine, mbarrier completion)
+//                      four steps ahead; a step is: wait for the slot, min over the label's entry list of
+//                      rep[k] + (L1 << S), add the unary term, publish the new key, one block barrier.
 //
 // Keys are 64 bit (dp << 32 | label): "smallest dp, lowest label on ties" (np.argmin, python bcd.py:155/:175/:234) is
-// one minimum, taken with the fp64 min instruction (see Key below).  32-bit keys relative to the running minimum were
+// one unsigned 64-bit minimum (see Key below).  32-bit keys relative to the running minimum were
 // tried first: because of quirk Q1 (the truncation candidate is ignored when S_l is not empty, :170-176) the spread of
 // dp over the labels of a pixel is not bounded, ~5 % of the row chains of the bench workload overflowed 22 bits and had
 // to be re-run, and a phase lasts as long as its slowest chain.
 //
-// A record that does not fit (arena exhausted, larger than a slot, data cost out of 22 bits) gets descriptor 0 and
+// A record that does not fit (arena exhausted, staging or slot too small, list longer than 127, data cost out of 16
+// bits) gets descriptor 0 and
 // its step is evaluated densely from pvec/cost inside the chain kernel, so any workspace size gives the exact result.
 #include <algorithm>
 #include <type_traits>
