@@ -429,11 +429,12 @@ struct ChainArgs {
   double lamda;
 };
 
+constexpr int kRepOff = 48 + 2 * 16 * 8;   // byte offset of rep_s in the chain kernel's shared memory
 constexpr int kSlotSlack = 1024;   // masked lanes of the entry loop may read (and ignore) this far past a record
 
 __host__ __device__ inline size_t chain_fixed_smem(int Kpad, int len) {
-  // mbar[4] | present[4] | trunc[4] | rep[2 * Kpad] keys | oldvec[len] | vprev[Kpad]; slots follow, 128-aligned
-  return (80 + 2 * (size_t)Kpad * 8 + 4 * (size_t)len + 4 * (size_t)Kpad + 127) & ~(size_t)127;
+  // mbar[4] | present[4] | wred[2][16] keys | rep[2 * Kpad] keys | oldvec[len] | vprev[Kpad]; slots follow, 128-aligned
+  return (kRepOff + 2 * (size_t)Kpad * 8 + 4 * (size_t)len + 4 * (size_t)Kpad + 127) & ~(size_t)127;
 }
 
 template <typename CostT, int T>
@@ -449,9 +450,9 @@ __device__ __forceinline__ void chain_body(const ChainArgs& a) {
 
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* present_s = reinterpret_cast<uint32_t*>(smem_raw + 32);
-  Key* trunc_s = reinterpret_cast<Key*>(smem_raw + 48);
-  Key* rep_s = reinterpret_cast<Key*>(smem_raw + 80);
-  int32_t* oldvec = reinterpret_cast<int32_t*>(smem_raw + 80 + 2 * (size_t)Kpad * 8);
+  Key* wred = reinterpret_cast<Key*>(smem_raw + 48);                          // [2][16] warp minima of a step
+  Key* rep_s = reinterpret_cast<Key*>(smem_raw + kRepOff);
+  int32_t* oldvec = reinterpret_cast<int32_t*>(smem_raw + kRepOff + 2 * (size_t)Kpad * 8);
   int32_t* vprev = oldvec + g.len;
   unsigned char* slots = smem_raw + chain_fixed_smem(Kpad, g.len);
 
@@ -461,7 +462,6 @@ __device__ __forceinline__ void chain_body(const ChainArgs& a) {
     const int p = pixel(i);
     oldvec[i] = a.pvec[(size_t)p * K + a.labels[p]];
   }
-  if (t < 4) trunc_s[t] = kKeyInf;
   if (t == 0) {
     for (int s = 0; s < S; ++s) ptx::mbar_init(&mbar[s], 1);
     ptx::fence_barrier_init();
@@ -486,8 +486,19 @@ __device__ __forceinline__ void chain_body(const ChainArgs& a) {
     if (S < g.len) d_next = dsc[pixel(S)];
   }
 
-  uint16_t* bp_row = a.bp + (size_t)blockIdx.x * g.len * Kpad;   // row of step i (advanced every step)
+  // Block minimum of the previous step's keys (+ tpsi): the truncation candidate min_k(tpsi + dp_prev[k]), lowest k on
+  // ties (:152-157).  Every warp leaves the minimum of its keys in wred[parity][warp] (no atomics: a 64-bit shared
+  // atomicMin is a compare-and-swap loop that ten warps would contend on every step); only the labels with an empty
+  // K-set read them -- and labels are stored by decreasing list length, so those sit in the last warp or two.
   const uint32_t tpsi_dp = (uint32_t)tpsi << shift;
+  int n_prev = 0;   // labels of the previous pixel (uniform)
+  auto trunc_of = [&](int step, int n_of_step) -> Key {
+    const Key* w = wred + (step & 1) * 16;
+    Key m = kKeyInf;
+    for (int k = 0; k * 32 < n_of_step; ++k) m = key_min(m, w[k]);
+    return key_add(m, tpsi_dp);
+  };
+  uint16_t* bp_row = a.bp + (size_t)blockIdx.x * g.len * Kpad;   // row of step i (advanced every step)
   const uint32_t l1_scale = 1u << shift;
 
   for (int i = 0; i < g.len; ++i, bp_row += Kpad) {
@@ -505,7 +516,6 @@ __device__ __forceinline__ void chain_body(const ChainArgs& a) {
       const uint4 hdr = *reinterpret_cast<const uint4*>(rec);
       const int n = (int)hdr.x;
       if (wfirst < n) {   // warps without labels only take part in the barrier
-        const Key trunc_prev = trunc_s[(i + 3) & 3];
         // unary side terms (sidepsi :84-88): the chain's own neighbours with their labels from before this call
         const int32_t ov_a = i + 1 < g.len ? oldvec[i + 1] : 0, ov_b = i > 0 ? oldvec[i - 1] : 0;
         if (t < n) {
@@ -532,7 +542,7 @@ __device__ __forceinline__ void chain_body(const ChainArgs& a) {
               e[2] = *reinterpret_cast<const uint16_t*>(ents + (R.y & 0xFFFFu));
               e[3] = *reinterpret_cast<const uint16_t*>(ents + (R.y >> 16));
             };
-            Key acc0 = len ? kKeyInf : trunc_prev;   // quirk Q1: the truncation candidate only when the K-set is empty
+            Key acc0 = len ? kKeyInf : trunc_of(i - 1, n_prev);   // quirk Q1: truncation only when the K-set is empty
             Key acc1 = kKeyInf, acc2 = kKeyInf, acc3 = kKeyInf;
             uint2 R = *reinterpret_cast<const uint2*>(roff);
             for (int r = 0; r < len; r += 4) {
@@ -559,11 +569,11 @@ __device__ __forceinline__ void chain_body(const ChainArgs& a) {
         }
         // block minimum of (dp + tpsi, label) for the next step's truncation candidate (:152-157), lowest label on ties
         const Key wmin = warp_min_key(key);
-        if (lane == 0 && wmin != kKeyInf) atomicMin(&trunc_s[i & 3], key_add(wmin, tpsi_dp));
+        if (lane == 0) wred[(i & 1) * 16 + (t >> 5)] = wmin;
       }
+      n_prev = n;
     } else {
       // dense step: the record was not stored; evaluate the K-set from the proposal arrays
-      const Key trunc_prev = trunc_s[(i + 3) & 3];
       const int32_t ov_a = i + 1 < g.len ? oldvec[i + 1] : 0, ov_b = i > 0 ? oldvec[i - 1] : 0;
       const int p = pixel(i);
       const int n = a.nprop[p];
@@ -589,7 +599,7 @@ __device__ __forceinline__ void chain_body(const ChainArgs& a) {
             const int l1 = l1_vec(dy, dx, vprev[k]);
             if (l1 < tpsi) acc = key_min(acc, key_add(rp[2 * k], (uint32_t)l1 << shift));
           }
-          if (acc == kKeyInf) acc = trunc_prev;
+          if (acc == kKeyInf) acc = trunc_of(i - 1, n_prev);
           dp = key_dp(acc) + U;
           bp_row[t] = (uint16_t)key_label(acc);
         }
@@ -597,9 +607,9 @@ __device__ __forceinline__ void chain_body(const ChainArgs& a) {
         rc[2 * t] = key;
       }
       const Key wmin = warp_min_key(key);
-      if (lane == 0 && wmin != kKeyInf) atomicMin(&trunc_s[i & 3], key_add(wmin, tpsi_dp));
+      if (lane == 0 && (t & ~31) < n) wred[(i & 1) * 16 + (t >> 5)] = wmin;
+      n_prev = n;
     }
-    if (t == 0) trunc_s[(i + 1) & 3] = kKeyInf;   // written at step i+1, last read at step i-2
     __syncthreads();
     if (t == 0 && i + S < g.len) {
       issue(i + S, d_next);
@@ -609,7 +619,7 @@ __device__ __forceinline__ void chain_body(const ChainArgs& a) {
 
   // final label: lowest-index argmin of dp_last (:231-237) = label field of the last block minimum; backtrack
   // (:238-253) through the back-pointers, staged through shared memory a segment of rows at a time
-  int lab = (int)key_label(trunc_s[(g.len - 1) & 3]);
+  int lab = (int)key_label(trunc_of(g.len - 1, n_prev));
   const int rows_cap = max(1, (int)(((size_t)S * a.slot_bytes) / ((size_t)Kpad * 2)));
   uint16_t* seg = reinterpret_cast<uint16_t*>(slots);
   const int vec_per_row = Kpad / 8;   // uint4 = 8 back-pointers
@@ -711,8 +721,8 @@ static int make_plan(int H, int W, int K, int tpsi, int shift, size_t workspace_
   if (!P->kern) return FLOWB200_EUNSUPPORTED;
   // ring of record slots: as many (<= 4) as keep `minb` chains per SM resident
   const int maxlen = H > W ? H : W;
-  // (masked lanes of the entry loop may also read up to 8272 bytes past the start of shared memory)
-  const size_t fixed = std::max(chain_fixed_smem(Kpad, maxlen) + kSlotSlack, (size_t)8448);
+  // (masked lanes of the entry loop may also read a stale key up to 8 KB past the start of rep_s)
+  const size_t fixed = std::max(chain_fixed_smem(Kpad, maxlen) + kSlotSlack, (size_t)kRepOff + 8192 + 64);
   // a slot holds the largest record the build kernel can stage: header, round offsets, n structs, staged entries
   P->slot_bytes =
       (uint32_t)((kRecHeader + 288 + 8 * (size_t)Kpad + 2 * (size_t)kStagePerLabel * Kpad + 127) & ~(size_t)127);
