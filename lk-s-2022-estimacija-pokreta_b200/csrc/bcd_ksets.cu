@@ -158,7 +158,10 @@ __host__ __device__ inline size_t build_smem_bytes(int Kpad) {
          (size_t)kStagePerLabel * Kpad * 2;
 }
 
-constexpr int kBuildThreads = 128;
+#ifndef FLOWB200_BUILD_THREADS
+#define FLOWB200_BUILD_THREADS 128
+#endif
+constexpr int kBuildThreads = FLOWB200_BUILD_THREADS;
 
 template <typename CostT>
 __global__ void __launch_bounds__(kBuildThreads)
@@ -222,7 +225,7 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
         kq3[s] = (uint16_t)((uint32_t)sq[s] << 4);
       }
     }
-    if (t < 128) hist[t] = 0;
+    for (int i = t; i < 128; i += kBuildThreads) hist[i] = 0;
     __syncthreads();
     // 2. every bucket's [first, last+1) range
     for (int s = t; s < nq; s += kBuildThreads) {
