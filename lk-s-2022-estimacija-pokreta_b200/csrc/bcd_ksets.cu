@@ -94,7 +94,7 @@ kset_sort_kernel(const int32_t* __restrict__ pvec, const int32_t* __restrict__ n
 }
 
 // ------------------------------------------------------------------------------------------------
-// build: one warp per record
+// build: one CTA (kBuildThreads threads) per record
 //
 // Record layout (16-byte aligned, at most one chain-kernel slot):
 //   [0,16)   uint32 n, nr (rounds = longest list), struct byte offset, entry byte offset
