@@ -108,7 +108,8 @@ kset_sort_kernel(const int32_t* __restrict__ pvec, const int32_t* __restrict__ n
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxList = 127;                  // list length field: 7 bits
 constexpr uint32_t kCostLimit16 = 1u << 16;    // data cost field: 16 bits
-constexpr int kStagePerLabel = 10;             // staging capacity: candidates per label of Kpad
+constexpr int kStagePerLabel = 16;             // staging capacity of the build kernel: candidates per label of Kpad
+constexpr int kSlotPerLabel = 12;              // chain-kernel slot capacity: stored entries per label of Kpad
 
 // previous pixel of `p` in the chain of orientation `orient` (0 = column chain, 1 = row chain) that visits it, or -1
 // at the start of the chain (python bcd.py:265-277: even columns run down, even rows right to left, odd columns up,
@@ -729,9 +730,9 @@ static int make_plan(int H, int W, int K, int tpsi, int shift, size_t workspace_
   const int maxlen = H > W ? H : W;
   // (masked lanes of the entry loop may also read a stale key up to 8 KB past the start of rep_s)
   const size_t fixed = std::max(chain_fixed_smem(Kpad, maxlen) + kSlotSlack, (size_t)kRepOff + 8192 + 64);
-  // a slot holds the largest record the build kernel can stage: header, round offsets, n structs, staged entries
+  // a slot holds header, round offsets, n structs and kSlotPerLabel entries per label; larger records go dense
   P->slot_bytes =
-      (uint32_t)((kRecHeader + 288 + 8 * (size_t)Kpad + 2 * (size_t)kStagePerLabel * Kpad + 127) & ~(size_t)127);
+      (uint32_t)((kRecHeader + 288 + 8 * (size_t)Kpad + 2 * (size_t)kSlotPerLabel * Kpad + 127) & ~(size_t)127);
   const size_t budget = (size_t)(227 * 1024) / minb - 1024;
   if (fixed + 4 * (size_t)P->slot_bytes > budget) P->slot_shift = 1;
   // long chains (large images): fewer resident chains rather than smaller slots
