@@ -224,26 +224,17 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
         const int32_t v = svq[s];
         vq2[s] = make_int2(vec_dy(v), vec_dx(v));
         kq3[s] = (uint16_t)((uint32_t)sq[s] << 4);
+        inv[s] = (uint16_t)bucket_key(v, bshift);
       }
     }
     for (int i = t; i < 128; i += kBuildThreads) hist[i] = 0;
     __syncthreads();
-    // 2. every bucket's [first, last+1) range
+    // 2. every bucket's [first, last+1) range (the bucket keys were left in `inv`, which is free until step 5)
     for (int s = t; s < nq; s += kBuildThreads) {
-      const int2 u = vq2[s];
-      const int key = (bkt_y(u.x >> bshift) << 6) | bkt_x(u.y >> bshift);
+      const int key = inv[s];
       uint16_t* half = reinterpret_cast<uint16_t*>(rng + key);
-      bool first = s == 0, last = s == nq - 1;
-      if (!first) {
-        const int2 a = vq2[s - 1];
-        first = ((bkt_y(a.x >> bshift) << 6) | bkt_x(a.y >> bshift)) != key;
-      }
-      if (!last) {
-        const int2 b = vq2[s + 1];
-        last = ((bkt_y(b.x >> bshift) << 6) | bkt_x(b.y >> bshift)) != key;
-      }
-      if (first) half[0] = (uint16_t)s;
-      if (last) half[1] = (uint16_t)(s + 1);
+      if (s == 0 || inv[s - 1] != key) half[0] = (uint16_t)s;
+      if (s == nq - 1 || inv[s + 1] != key) half[1] = (uint16_t)(s + 1);
     }
     __syncthreads();
 
@@ -389,11 +380,10 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
         for (int r = 0; r < len; ++r) ents[roff[r] + pos] = src[r];
       }
     }
-    // 7. empty the touched buckets and the per-record state for the next record
-    for (int s = t; s < nq; s += kBuildThreads) {
-      const int2 u = vq2[s];
-      rng[(bkt_y(u.x >> bshift) << 6) | bkt_x(u.y >> bshift)] = kRngEmpty;
-    }
+    // 7. empty the bucket table (4 KB: two 16-byte stores per thread) and the per-record state for the next record
+    if (q >= 0)
+      for (int i = t; i < kHashSize / 4; i += kBuildThreads)
+        reinterpret_cast<uint4*>(rng)[i] = make_uint4(kRngEmpty, kRngEmpty, kRngEmpty, kRngEmpty);
     if (t < 2) misc[t] = 0;
     __syncthreads();
   }
