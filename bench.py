@@ -30,6 +30,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's own messages (it prints its version on stdout when NCCL_DEBUG is set
+# by the environment) go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 PKG = "lk-s-2022-estimacija-pokreta_b200"
 
 WORKLOADS = {
