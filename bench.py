@@ -30,9 +30,16 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's own messages (it prints its version on stdout when NCCL_DEBUG is set
-# by the environment) go to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line.  Libraries write there too (NCCL prints "NCCL version ..." on stdout when
+# the environment sets NCCL_DEBUG=VERSION, as the GPU boxes do): file descriptor 1 is pointed at stderr for the whole
+# run and the JSON line goes to a duplicate of the original stdout.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 PKG = "lk-s-2022-estimacija-pokreta_b200"
 
 WORKLOADS = {
@@ -218,7 +225,7 @@ def run_reference(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_huge(args):
@@ -312,7 +319,7 @@ def run_huge(args):
                              "peak_source": pk["src"] + " (MEASURED_PEAKS.json) x n_gpus",
                              "note": "algorithmic FLOPs of the full-image search / max-over-ranks time of search + merge"},
                 "cpu_baseline": None}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -474,7 +481,7 @@ def main():
                         "d2h_bytes_per_step": p.H * p.W * 12},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
                 "accuracy": accuracy}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
