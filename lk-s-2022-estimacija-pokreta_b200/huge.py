@@ -5,8 +5,9 @@ columns, one band per rank.  A rank searches only its band (plus nothing else: i
 its band and the source descriptors to the columns whose +-cell_radius window reaches the band, and runs the
 ordinary per-cell exact search on that sub-image).  In the reference's slot order (daisy i flann.py:162-177: cell
 column major, cell row minor, then rank) the proposals one source pixel gets from one band are ONE contiguous slot
-range, so the "merge of per-GPU top-K lists" is not a comparison merge: every rank broadcasts its block and every
-rank copies slot ranges into place (`merge_bands`, NCCL over NVLink; gloo in the CPU tests).  BCD shards too: the
+range, so the "merge of per-GPU top-K lists" is not a comparison merge: every rank packs the slot ranges of its band,
+one all-gather moves them, and every rank copies slot ranges into place (`merge_bands`, NCCL over NVLink; gloo in the
+CPU tests).  BCD shards too: the
 chains of a phase are independent, every rank runs a contiguous share of them and one all-reduce of the label
 differences per phase gives every rank the phase's result (`bcd_sharded`).  DAISY, the random proposals and the
 consistency check are cheap and run replicated, with identical results on every rank.
@@ -108,33 +109,72 @@ def nn_counts(p: FlowParams):
     return (p.k_cell * ny[:, None] * nx[None, :]).astype(np.int32)
 
 
+def _plan_elems(plan):
+    return sum((y1 - y0) * (x1 - x0) * n for y0, y1, x0, x1, _, _, n in plan)
+
+
+def pack_band(p: FlowParams, b: Band, sub_pvec, sub_lcost, out):
+    """The slot ranges of band `b` that the merge needs (copy_plan order), vectors then costs (viewed as int32), into the
+    flat int32 buffer `out`: what a rank sends instead of its whole (halo columns, unused slots) block."""
+    plan = copy_plan(p, b)
+    half = _plan_elems(plan)
+    lc_i = sub_lcost.view(sub_pvec.dtype)
+    o = 0
+    for y0, y1, x0, x1, _, s0, n in plan:
+        cnt = (y1 - y0) * (x1 - x0) * n
+        out[o:o + cnt].view(y1 - y0, x1 - x0, n).copy_(sub_pvec[y0:y1, x0 - b.sx0:x1 - b.sx0, s0:s0 + n])
+        out[half + o:half + o + cnt].view(y1 - y0, x1 - x0, n).copy_(lc_i[y0:y1, x0 - b.sx0:x1 - b.sx0, s0:s0 + n])
+        o += cnt
+    return 2 * half
+
+
+def unpack_band(p: FlowParams, b: Band, flat, pvec, lcost):
+    """Inverse of pack_band into the full-image arrays."""
+    plan = copy_plan(p, b)
+    half = _plan_elems(plan)
+    lc_i = lcost.view(pvec.dtype)
+    o = 0
+    for y0, y1, x0, x1, d0, _, n in plan:
+        cnt = (y1 - y0) * (x1 - x0) * n
+        pvec[y0:y1, x0:x1, d0:d0 + n] = flat[o:o + cnt].view(y1 - y0, x1 - x0, n)
+        lc_i[y0:y1, x0:x1, d0:d0 + n] = flat[half + o:half + o + cnt].view(y1 - y0, x1 - x0, n)
+        o += cnt
+
+
 def merge_bands(p: FlowParams, bands, rank, sub_pvec, sub_lcost, device, dist=None, blocks=None):
-    """Every rank broadcasts its band block; every rank assembles the full proposal set.
+    """Every rank contributes the slot ranges of its band (packed, no halo columns, no unused slots) to ONE all-gather;
+    every rank unpacks all bands into the full proposal set.
 
     sub_pvec int32 / sub_lcost float32: (H, band width, K) of THIS rank (None for an empty band).
-    blocks (tests): {rank: (pvec, lcost)} of the other ranks, instead of broadcasting.
+    blocks (tests): {rank: (pvec, lcost)} of the other ranks, packed and unpacked locally instead of the all-gather.
     Returns (pvec (H,W,K) int32 filled -1, lcost (H,W,K) float32 filled 1000, nprop int32, labels int32) where
     labels is the first strict argmin of the data cost (daisy i flann.py:181-184)."""
     import torch
     H, W, K = p.H, p.W, p.maxnprop
     pvec = torch.full((H, W, K), -1, dtype=torch.int32, device=device)
     lcost = torch.full((H, W, K), 1000.0, dtype=torch.float32, device=device)
+    sizes = [2 * _plan_elems(copy_plan(p, b)) for b in bands]
+    cap = max(max(sizes), 1)
+    world = len(bands)
+    send = torch.empty(cap, dtype=torch.int32, device=device)
+    if sizes[rank]:
+        pack_band(p, bands[rank], sub_pvec, sub_lcost, send)
+    if blocks is not None or dist is None or world == 1:
+        recv = torch.empty((world, cap), dtype=torch.int32, device=device)
+        recv[rank] = send
+        if blocks is not None:
+            for b in bands:
+                if b.rank != rank and sizes[b.rank]:
+                    pack_band(p, b, blocks[b.rank][0], blocks[b.rank][1], recv[b.rank])
+    else:
+        recv = torch.empty((world, cap), dtype=torch.int32, device=device)
+        try:
+            dist.all_gather_into_tensor(recv.view(-1), send)
+        except (RuntimeError, AttributeError, NotImplementedError):
+            dist.all_gather([recv[r] for r in range(world)], send)
     for b in bands:
-        if b.ci_hi <= b.ci_lo:
-            continue
-        if b.rank == rank:
-            bp, bc = sub_pvec.contiguous(), sub_lcost.contiguous()
-        elif blocks is not None:
-            bp, bc = blocks[b.rank]
-        else:
-            bp = torch.empty((H, b.width, K), dtype=torch.int32, device=device)
-            bc = torch.empty((H, b.width, K), dtype=torch.float32, device=device)
-        if dist is not None and blocks is None and len(bands) > 1:
-            dist.broadcast(bp, src=b.rank)
-            dist.broadcast(bc, src=b.rank)
-        for y0, y1, x0, x1, d0, s0, n in copy_plan(p, b):
-            pvec[y0:y1, x0:x1, d0:d0 + n] = bp[y0:y1, x0 - b.sx0:x1 - b.sx0, s0:s0 + n]
-            lcost[y0:y1, x0:x1, d0:d0 + n] = bc[y0:y1, x0 - b.sx0:x1 - b.sx0, s0:s0 + n]
+        if sizes[b.rank]:
+            unpack_band(p, b, recv[b.rank], pvec, lcost)
     nprop = torch.from_numpy(nn_counts(p)).to(device)
     # first strict argmin: costs are >= 0, so the float bit pattern orders like the value; the slot breaks ties
     labels = torch.empty((H, W), dtype=torch.int32, device=device)
