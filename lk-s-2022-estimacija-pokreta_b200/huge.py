@@ -201,12 +201,14 @@ def knn_proposals_sharded(desc_src, desc_tgt, p: FlowParams, rank, world, dist=N
     return merge_bands(p, bands, rank, sub_pvec, sub_lcost, desc_src.device, dist)
 
 
-def bcd_sharded(pvec, cost, nprop, labels, sweeps, p: FlowParams, mode, rank, world, dist=None):
+def bcd_sharded(pvec, cost, nprop, labels, sweeps, p: FlowParams, mode, rank, world, dist=None, ops=None):
     """ceoBCD with every phase's chains split over the ranks.  The chains of a phase are independent (they read and
     write only their own pixels), so a rank runs its share and the ranks then exchange what changed: every rank holds
     the full label image, `new - old` is zero outside the rank's own chains, and one all-reduce(sum) of that difference
-    per phase (4 bytes per pixel over NVLink) gives every rank the phase's result."""
-    from . import ops
+    per phase (4 bytes per pixel over NVLink) gives every rank the phase's result.
+    `ops` (tests): a stand-in for the device operators with the same bcd_workspace / bcd_prepare / bcd_phase."""
+    if ops is None:
+        from . import ops
     ws = ops.bcd_workspace(pvec)
     kw = dict(mode=mode, lamda=p.lamda, tpsi=p.tpsi, cost_shift=p.cost_shift)
     ops.bcd_prepare(pvec, cost, nprop, ws, rank, world, **kw)

@@ -120,3 +120,62 @@ def test_sharded_bcd_phases_with_delta_exchange_equal_full_sweeps(world):
                 labels[r] = labels[r] + total
     for r in range(world):
         assert np.array_equal(labels[r], want)
+
+
+class _OracleOps:
+    """CPU stand-in for ops.bcd_workspace / bcd_prepare / bcd_phase: the oracle's _phase on the owned chains."""
+
+    def __init__(self, prop, lc, nprop):
+        self.prop, self.lc, self.nprop = prop, lc, nprop
+
+    def bcd_workspace(self, pvec):
+        return None
+
+    def bcd_prepare(self, *a, **k):
+        pass
+
+    def bcd_phase(self, pvec, cost, nprop, labels, ws, phase, part, nparts, **kw):
+        from oracle import bcd as obcd
+        H, W = labels.shape
+        geo = [(1, 0, [(0, x) for x in range(0, W, 2)]), (0, -1, [(y, W - 1) for y in range(0, H, 2)]),
+               (-1, 0, [(H - 1, x) for x in range(1, W, 2)]), (0, 1, [(y, 0) for y in range(1, H, 2)])][phase]
+        n = len(geo[2])
+        mine = geo[2][n * part // nparts:n * (part + 1) // nparts]     # owned_chains() of csrc/bcd_ksets.cu
+        if mine:
+            lab = labels.numpy().astype(np.int64)
+            obcd._phase(self.prop, self.lc, self.nprop, lab, 8, 0.05, geo[0], geo[1], mine)
+            labels.copy_(__import__("torch").from_numpy(lab.astype(np.int32)))
+
+
+def test_two_gloo_ranks_bcd_sharded(tmp_path):
+    """huge.bcd_sharded itself (per-phase label difference all-reduce) over two gloo ranks, the oracle standing in
+    for the device operators: both ranks end with the oracle's full sweeps."""
+    pytest.importorskip("torch")
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        import numpy as np, torch, torch.distributed as dist
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, os.path.join({ROOT!r}, "tests"))
+        from helpers import pkg
+        from oracle import bcd as obcd
+        from test_huge_plan import _OracleOps
+        params, huge = pkg("params"), pkg("huge")
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        rng = np.random.default_rng(9)
+        H, W, K = 8, 10, 10
+        prop = rng.integers(-6, 7, (H, W, K, 2)).astype(np.int64)
+        nprop = rng.integers(3, K + 1, (H, W)).astype(np.int64)
+        lc = 20.0 * rng.integers(0, 513, (H, W, K)) / 4096.0
+        lab0 = (rng.integers(0, 1 << 20, (H, W)) % nprop).astype(np.int64)
+        want = obcd.ceo_bcd(prop, lc, nprop, lab0, 2)[-1]
+        labels = torch.from_numpy(lab0.astype(np.int32))
+        p = params.FlowParams(H=H, W=W, cellw=4, cellh=4, maxnprop=K, n_gauss=0, k_cell=1, cell_radius=0)
+        huge.bcd_sharded(None, None, None, labels, 2, p, 3, rank, world, dist, ops=_OracleOps(prop, lc, nprop))
+        open(os.path.join({str(tmp_path)!r}, f"ok{{rank}}"), "w").write(str(np.array_equal(labels.numpy(), want)))
+    """))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29543", str(script)],
+                       capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert open(tmp_path / "ok0").read() == "True" and open(tmp_path / "ok1").read() == "True"
