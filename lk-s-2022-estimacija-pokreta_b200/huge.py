@@ -209,7 +209,7 @@ def bcd_sharded(pvec, cost, nprop, labels, sweeps, p: FlowParams, mode, rank, wo
     `ops` (tests): a stand-in for the device operators with the same bcd_workspace / bcd_prepare / bcd_phase."""
     if ops is None:
         from . import ops
-    ws = ops.bcd_workspace(pvec)
+    ws = ops.bcd_workspace(pvec, world)
     kw = dict(mode=mode, lamda=p.lamda, tpsi=p.tpsi, cost_shift=p.cost_shift)
     ops.bcd_prepare(pvec, cost, nprop, ws, rank, world, **kw)
     for _ in range(sweeps):

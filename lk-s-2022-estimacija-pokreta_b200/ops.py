@@ -141,10 +141,17 @@ def bcd(pvec, cost, nprop, labels, sweeps, mode=_lib.BCD_FP64_F32COST, lamda=0.0
     return snaps
 
 
-def bcd_workspace(pvec):
+def bcd_workspace(pvec, nparts=1):
+    """Workspace for flowb200_bcd / flowb200_bcd_prepare.  A part of `nparts` stores only the records of its own chains,
+    so its record arena is the recommended size divided by nparts (plus slack); whatever does not fit is evaluated on
+    the fly (any size between the minimum and the recommended one gives the same labels)."""
     lib = _lib.load()
     H, W, K = pvec.shape
-    return _workspace(lib.flowb200_bcd_workspace_bytes(H, W, K), pvec.device)
+    full = lib.flowb200_bcd_workspace_bytes(H, W, K)
+    if nparts > 1:
+        lo = lib.flowb200_bcd_min_workspace_bytes(H, W, K)
+        full = min(full, lo + int((full - lo) * 1.3 / nparts) + (1 << 20))
+    return _workspace(full, pvec.device)
 
 
 def bcd_prepare(pvec, cost, nprop, ws, part=0, nparts=1, mode=_lib.BCD_INT32_F32COST, lamda=0.05, tpsi=8, cost_shift=12):

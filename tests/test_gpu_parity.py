@@ -439,7 +439,7 @@ def test_bcd_in_pieces_equals_whole(nparts):
     pvec = dev(ioc.pack_proposals(z["proposals"]))
     m, nprop = dev(z["m"], torch.int32), dev(z["nprop"], torch.int32)
     kw = dict(mode=lib.BCD_INT32, cost_shift=shift)
-    wss = [ops.bcd_workspace(pvec).clone() for _ in range(nparts)]
+    wss = [ops.bcd_workspace(pvec, nparts).clone() for _ in range(nparts)]   # a part's share of the record arena
     for r in range(nparts):
         ops.bcd_prepare(pvec, m, nprop, wss[r], r, nparts, **kw)
     labels = dev(z["labels00"], torch.int32)

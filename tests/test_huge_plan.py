@@ -128,7 +128,7 @@ class _OracleOps:
     def __init__(self, prop, lc, nprop):
         self.prop, self.lc, self.nprop = prop, lc, nprop
 
-    def bcd_workspace(self, pvec):
+    def bcd_workspace(self, pvec, nparts=1):
         return None
 
     def bcd_prepare(self, *a, **k):
