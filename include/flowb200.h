@@ -162,6 +162,15 @@ int flowb200_flow_from_labels(const int32_t* pvec, const int32_t* labels, int H,
 int flowb200_consistency(float* flow1, const float* flow2, int A, int B, float tresh,
                          int a0, int a1, int b0, int b1, flowb200_stream_t stream);
 
+/* ---- removeSmallSegments (postprocessing.py:29-76; disabled in the reference's postProcessing, :132) ----
+ * flow (in place): float32 [A][B][3] = (dx, dy, valid).  Flood fill over 4-neighbours whose float32 L1 flow difference
+ * is <= tresh; a segment with 1 < pixels < min_segment_size loses its valid flags (the flow components stay).  The
+ * reference's scan-order effects (invalid seeds, the column rebinding of :74) are reproduced bit for bit: connected
+ * components are labelled in parallel, the scan itself is replayed by one warp (csrc/segments_core.cuh). */
+size_t flowb200_segments_workspace_bytes(int A, int B);
+int flowb200_remove_small_segments(float* flow, int A, int B, float tresh, int min_segment_size, void* workspace,
+                                   size_t workspace_bytes, flowb200_stream_t stream);
+
 /* ---- metric: visualization.errorImage (visualization.py:128-152), the EPE definition of the benchmark ----
  * test/gt: float32 [H][W][3] = (u, v, valid).  out3 (device float64[3]) = {sum of end-point errors over pixels valid
  * in both, number of them with error > abs_thresh (3.0 in the reference), number of pixels valid in both}. */
@@ -190,6 +199,9 @@ int flowb200_ctx_flow_pair_host(flowb200_ctx* ctx, const uint8_t* bgr0_host, con
 /* postprocessing.fowardBackwardConsistency on host arrays (flow1_host modified in place). */
 int flowb200_consistency_host(float* flow1_host, const float* flow2_host, int A, int B, float tresh,
                               int a0, int a1, int b0, int b1);
+
+/* postprocessing.removeSmallSegments on a host array (flow_host modified in place). */
+int flowb200_remove_small_segments_host(float* flow_host, int A, int B, float tresh, int min_segment_size);
 
 #ifdef __cplusplus
 }

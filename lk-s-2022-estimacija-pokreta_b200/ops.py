@@ -197,6 +197,20 @@ def consistency(flow1, flow2, tresh, region=None):
     return flow1
 
 
+def remove_small_segments(flow, tresh, min_segment_size, workspace=None):
+    """removeSmallSegments (postprocessing.py:29-76), in place on flow (float32 (A,B,3) device tensor)."""
+    lib = _lib.load()
+    A, B, ch = flow.shape
+    assert ch == 3
+    need = int(lib.flowb200_segments_workspace_bytes(A, B))
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=flow.device)
+    _lib.check(lib.flowb200_remove_small_segments(_ptr(flow, torch.float32, "flow"), A, B, float(tresh),
+                                                  int(min_segment_size), _ptr(workspace), workspace.numel(),
+                                                  _stream()), "flowb200_remove_small_segments")
+    return flow
+
+
 def epe(test_uvv, gt_uvv, abs_thresh=3.0):
     """visualization.errorImage (visualization.py:128-152): (mean EPE, outlier %, n_valid) over pixels valid in both."""
     lib = _lib.load()

@@ -2,12 +2,17 @@
 
 Same names, arguments, in-place semantics and output as the reference:
   FlowImage().ucitajFlow(path)                       :5-17     .npy only; [dy,dx] -> (dx, dy, 1) float32
-  consistencyCheck(flow1, flow2, u1, v1, tresh)      :79-110   one pixel, in place on flow1.flow
+  removeSmallSegments(flow, tresh, min_segment_size) :29-76    in place on flow (disabled in the reference's own
+                                                               postProcessing, :132)
+  consistencyCheck(flow1, flow2, u1, v1, tresh)      :79-110   one pixel, in place on flow1
   fowardBackwardConsistency(flow1, flow2, tresh)     :114-117  every pixel of flow1
   postProcessing(filename1, filename2, con_tresh, npysave) -> FlowImage   :123-135
-The checks run on the GPU through flowb200_consistency (quirk Q5 reproduced); there is no CPU fallback.
-removeSmallSegments (:29-76) is disabled in the reference (:132) and is not part of the hot path.
+`flow`, `flow1`, `flow2` are float32 (H,W,3) arrays = (dx, dy, valid) as in the reference, whose callers pass
+`FlowImage.flow` (:133); a FlowImage itself is accepted too.  The work runs on the GPU through
+flowb200_consistency_host / flowb200_remove_small_segments_host (quirk Q5 and the scan-order effects of
+removeSmallSegments reproduced); there is no CPU fallback.
 """
+import math
 import os
 import sys
 
@@ -35,11 +40,34 @@ class FlowImage:
             print("Unknown file format!")
 
 
+def _field(flow, name):
+    """The (H,W,3) array behind an argument: the array itself (what the reference's callers pass) or FlowImage.flow."""
+    f = flow.flow if isinstance(flow, FlowImage) else flow
+    if not isinstance(f, np.ndarray) or f.ndim != 3 or f.shape[2] != 3:
+        raise TypeError(f"{name} must be an (H,W,3) array or a FlowImage")
+    return f
+
+
+def _inplace_field(flow, name):
+    f = _field(flow, name)
+    if f.dtype != np.float32 or not f.flags.c_contiguous or not f.flags.writeable:
+        raise TypeError(f"{name} is modified in place: it must be a writeable C-contiguous float32 array")
+    return f
+
+
+def removeSmallSegments(flow, tresh, min_segment_size):
+    """In place on flow, returns None like the reference (:29-76)."""
+    f = _inplace_field(flow, "flow")
+    L = _lib.load()
+    # `1 < count < min_segment_size` (:73) with an integer count: a fractional bound acts like its ceiling
+    bound = max(0, min(int(math.ceil(min_segment_size)), 2**31 - 1))
+    _lib.check(L.flowb200_remove_small_segments_host(f.ctypes.data, f.shape[0], f.shape[1], float(tresh), bound),
+               "flowb200_remove_small_segments_host")
+
+
 def _check_region(flow1, flow2, a0, a1, b0, b1, tresh):
-    f1 = flow1.flow
-    if f1.dtype != np.float32 or not f1.flags.c_contiguous:
-        raise TypeError("flow1.flow must be a C-contiguous float32 array")
-    f2 = np.ascontiguousarray(flow2.flow, dtype=np.float32)
+    f1 = _inplace_field(flow1, "flow1")
+    f2 = np.ascontiguousarray(_field(flow2, "flow2"), dtype=np.float32)
     A, B = f1.shape[0], f1.shape[1]
     if f2 is f1 or np.shares_memory(f1, f2):
         f2 = f2.copy()
@@ -50,13 +78,15 @@ def _check_region(flow1, flow2, a0, a1, b0, b1, tresh):
 
 def consistencyCheck(flow1, flow2, u1, v1, tresh):
     """One pixel (u1, v1) = (row, col) of flow1, in place; returns None like the reference."""
-    if u1 < 0 or v1 < 0 or u1 >= flow1.flow.shape[0] or v1 >= flow1.flow.shape[1]:
+    shp = _field(flow1, "flow1").shape
+    if u1 < 0 or v1 < 0 or u1 >= shp[0] or v1 >= shp[1]:
         raise IndexError("index out of bounds")
     _check_region(flow1, flow2, int(u1), int(u1) + 1, int(v1), int(v1) + 1, tresh)
 
 
 def fowardBackwardConsistency(flow1, flow2, tresh):
-    _check_region(flow1, flow2, 0, flow1.flow.shape[0], 0, flow1.flow.shape[1], tresh)
+    shp = _field(flow1, "flow1").shape
+    _check_region(flow1, flow2, 0, shp[0], 0, shp[1], tresh)
 
 
 def postProcessing(filename1, filename2, con_tresh, npysave):
@@ -64,7 +94,8 @@ def postProcessing(filename1, filename2, con_tresh, npysave):
     flow1.ucitajFlow(filename1)
     flow2 = FlowImage()
     flow2.ucitajFlow(filename2)
-    fowardBackwardConsistency(flow1, flow2, con_tresh)
+    # removeSmallSegments(flow1.flow, 10, 100) is commented out in the reference (:132)
+    fowardBackwardConsistency(flow1.flow, flow2.flow, con_tresh)
     np.save(npysave, flow1.flow)
     return flow1
 

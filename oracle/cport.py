@@ -97,3 +97,14 @@ def forward_backward_consistency(flow1, flow2, tresh):
     A, B, _ = f1.shape
     lib().fo_consistency(_p(f1), _p(f2), A, B, C.c_float(tresh))
     return f1
+
+
+def remove_small_segments(flow, tresh, min_segment_size, want_count=False):
+    """removeSmallSegments (postprocessing.py:29-76) on a copy of flow; returns the modified copy."""
+    f = np.array(flow, dtype=np.float32, copy=True)
+    A, B, _ = f.shape
+    nrem = C.c_int32(0)
+    rc = lib().fo_remove_small_segments(_p(f), A, B, C.c_float(tresh), int(min_segment_size), C.byref(nrem))
+    if rc:
+        raise RuntimeError(f"fo_remove_small_segments failed: {rc}")
+    return (f, int(nrem.value)) if want_count else f

@@ -6,6 +6,7 @@
  *                   exact float64 brute force (ties -> lowest index), the search the north star prescribes
  *   fo_bcd          python bcd.py:84-88 (sidepsi), :98-99 (purepsi), :101-257 (bcd), :261-284 (ceoBCD)
  *   fo_consistency  postprocessing.py:79-117 (consistencyCheck / fowardBackwardConsistency)
+ *   fo_remove_small_segments  postprocessing.py:29-76 (removeSmallSegments, scan-order quirks included)
  * It is pinned by tests/test_oracle_c.py against tests/golden/ (outputs of the reference's own source).
  * OpenMP parallelises over independent units only (cells' query bands, chains of one phase, pixels),
  * so results do not depend on the thread count.
@@ -250,6 +251,55 @@ int fo_consistency(float* f1, const float* f2, int A, int B, float tresh) {
       if (bad) p[0] = p[1] = p[2] = 0.f;
     }
   }
+  return 0;
+}
+
+/* removeSmallSegments (postprocessing.py:29-76), in place on f: float32 [A][B][3] = (dx, dy, valid).
+ * A = shape[0] (the reference calls it `width`), B = shape[1] (`height`).  Sequential by nature; what is kept:
+ *  - seeds are visited column by column (outer index b, inner index a, :36-37) and a seed need not be valid (:41-43);
+ *  - a neighbour joins when it is unvisited, valid and its float32 L1 flow difference to the CURRENT pixel is
+ *    <= tresh (:62-65); neighbour order a-1, a+1, b-1, b+1 (:50-58);
+ *  - a segment with 1 < count < min_size loses its valid flags (:73-75), the flow components stay;
+ *  - the removal loop `for u, v in zip(...)` (:74) rebinds the scan's own `v`: the rest of the current column scan
+ *    reads column b = (second index of the segment's LAST pixel) until the outer loop advances.
+ * n_removed (optional): number of segments removed. */
+int fo_remove_small_segments(float* f, int A, int B, float tresh, int min_size, int32_t* n_removed) {
+  const size_t n = (size_t)A * B;
+  uint8_t* check = (uint8_t*)calloc(n, 1);
+  int32_t* q = (int32_t*)malloc(n * sizeof(int32_t));
+  if (!check || !q) { free(check); free(q); return -1; }
+  int removed = 0;
+  for (int bo = 0; bo < B; ++bo) {
+    int b = bo;
+    for (int a = 0; a < A; ++a) {
+      if (check[(size_t)a * B + b]) continue;
+      int count = 1, curr = 0;
+      q[0] = a * B + b;
+      while (curr < count) {
+        const int c = q[curr], ca = c / B, cb = c % B;
+        const float* fc = f + (size_t)c * 3;
+        const int na[4] = {ca - 1, ca + 1, ca, ca}, nb[4] = {cb, cb, cb - 1, cb + 1};
+        for (int t = 0; t < 4; ++t) {
+          if (na[t] < 0 || nb[t] < 0 || na[t] >= A || nb[t] >= B) continue;
+          const int m = na[t] * B + nb[t];
+          const float* fm = f + (size_t)m * 3;
+          if (check[m] || !(fm[2] > 0.5f)) continue;
+          const float d = fabsf(fc[0] - fm[0]) + fabsf(fc[1] - fm[1]);
+          if (d <= tresh) { q[count++] = m; check[m] = 1; }
+        }
+        ++curr;
+        check[c] = 1;
+      }
+      if (count > 1 && count < min_size) {
+        for (int i = 0; i < count; ++i) f[(size_t)q[i] * 3 + 2] = 0.f;
+        b = q[count - 1] % B;
+        ++removed;
+      }
+    }
+  }
+  if (n_removed) *n_removed = removed;
+  free(check);
+  free(q);
   return 0;
 }
 

@@ -7,6 +7,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 _m = importlib.import_module("lk-s-2022-estimacija-pokreta_b200.postprocessing")
 FlowImage = _m.FlowImage
+removeSmallSegments = _m.removeSmallSegments
 consistencyCheck = _m.consistencyCheck
 fowardBackwardConsistency = _m.fowardBackwardConsistency
 postProcessing = _m.postProcessing

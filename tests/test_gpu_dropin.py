@@ -111,9 +111,18 @@ def test_postprocessing_module_dropin(tmp_path):
     f1, f2 = pp.FlowImage(), pp.FlowImage()
     f1.ucitajFlow(str(tmp_path / "real_f.npy"))
     f2.ucitajFlow(str(tmp_path / "real_b.npy"))
+    # the reference's callers pass the arrays (postprocessing.py:133); a FlowImage is accepted as well
     for a in range(f1.height):
         for bb in range(0, f1.width, 3):
-            assert pp.consistencyCheck(f1, f2, a, bb, z["real_thr"].item()) is None
+            assert pp.consistencyCheck(f1.flow, f2.flow, a, bb, z["real_thr"].item()) is None
     assert np.array_equal(f1.flow[:, ::3], z["real_out"][:, ::3])
+    assert pp.consistencyCheck(f1, f2, 0, 1, z["real_thr"].item()) is None
+    assert np.array_equal(f1.flow[0, 1], z["real_out"][0, 1])
+    g1 = pp.FlowImage()
+    g1.ucitajFlow(str(tmp_path / "real_f.npy"))
+    assert pp.fowardBackwardConsistency(g1.flow, f2.flow, z["real_thr"].item()) is None
+    assert np.array_equal(g1.flow, z["real_out"])
     with pytest.raises(IndexError):
-        pp.consistencyCheck(f1, f2, f1.height, 0, 10)
+        pp.consistencyCheck(f1.flow, f2.flow, f1.height, 0, 10)
+    with pytest.raises(TypeError):
+        pp.fowardBackwardConsistency(g1.flow.astype(np.float64), f2.flow, 10)

@@ -73,3 +73,16 @@ def test_c_consistency_golden():
         out = cport.forward_backward_consistency(ocons.ucitaj_flow(z[k + "_fwd"]), ocons.ucitaj_flow(z[k + "_bwd"]),
                                                  float(z[k + "_thr"]))
         assert np.array_equal(out, z[k + "_out"]), k
+
+
+def test_c_remove_small_segments_golden():
+    """fo_remove_small_segments vs the reference's own removeSmallSegments (tests/golden/make_golden_segments.py)."""
+    z = load_npz("segments")
+    changed = 0
+    for i in range(int(z["n"])):
+        f, (tresh, ms) = z[f"c{i}_in"], z[f"c{i}_par"]
+        out = cport.remove_small_segments(f, float(tresh), int(ms))
+        assert np.array_equal(out[..., :2], f[..., :2])
+        assert np.array_equal(out[..., 2], z[f"c{i}_valid_out"].astype(np.float32)), i
+        changed += int((out[..., 2] != f[..., 2]).sum())
+    assert changed > 3000     # the fixtures do remove segments
