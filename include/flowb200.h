@@ -171,6 +171,14 @@ size_t flowb200_segments_workspace_bytes(int A, int B);
 int flowb200_remove_small_segments(float* flow, int A, int B, float tresh, int min_segment_size, void* workspace,
                                    size_t workspace_bytes, flowb200_stream_t stream);
 
+/* ---- edge.canny_ivice (edge.py:19-35): EpicFlow's edge input ----
+ * bgr: uint8 [H][W][3].  inverted_edges: float32 [H][W], 0.0f on an edge, 1.0f elsewhere (edge.py:29).
+ * cvtColor(BGR2GRAY) -> GaussianBlur(3x3, sigma 0) -> Canny(low, high) (the reference passes 100, 200), L1 gradient,
+ * aperture 3: OpenCV's 8-bit integer arithmetic, bit-identical (csrc/edges_core.cuh). */
+size_t flowb200_edges_workspace_bytes(int H, int W);
+int flowb200_canny_edges(const uint8_t* bgr, int H, int W, int low, int high, float* inverted_edges, void* workspace,
+                         size_t workspace_bytes, flowb200_stream_t stream);
+
 /* ---- metric: visualization.errorImage (visualization.py:128-152), the EPE definition of the benchmark ----
  * test/gt: float32 [H][W][3] = (u, v, valid).  out3 (device float64[3]) = {sum of end-point errors over pixels valid
  * in both, number of them with error > abs_thresh (3.0 in the reference), number of pixels valid in both}. */
@@ -202,6 +210,9 @@ int flowb200_consistency_host(float* flow1_host, const float* flow2_host, int A,
 
 /* postprocessing.removeSmallSegments on a host array (flow_host modified in place). */
 int flowb200_remove_small_segments_host(float* flow_host, int A, int B, float tresh, int min_segment_size);
+
+/* edge.canny_ivice on host arrays (bgr_host uint8 [H][W][3] -> inverted_edges_host float32 [H][W]). */
+int flowb200_canny_edges_host(const uint8_t* bgr_host, int H, int W, int low, int high, float* inverted_edges_host);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,8 @@ SYMBOLS = {
     "flowb200_consistency": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "flowb200_segments_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "flowb200_remove_small_segments": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_int, _P, C.c_size_t, _P]),
+    "flowb200_edges_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "flowb200_canny_edges": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     "flowb200_epe": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P]),
     "flowb200_pair_workspace_bytes": (C.c_size_t, [_PP]),
     "flowb200_flow_pair": (C.c_int, [_P, _P, _PP, C.c_int, C.c_int, C.c_uint64, _P, _P, _P, _P, C.c_size_t, _P]),
@@ -65,6 +67,7 @@ SYMBOLS = {
     "flowb200_ctx_flow_pair_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_uint64, _P]),
     "flowb200_consistency_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]),
     "flowb200_remove_small_segments_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_int]),
+    "flowb200_canny_edges_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }
 
 _lib = None

@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "segments_core.cuh"
+#include "unionfind.cuh"
 
 namespace flowb200 {
 namespace {
@@ -57,46 +58,21 @@ __global__ void seg_init_kernel(const float* __restrict__ flow, int A, int B, fl
   vis[s] = 0;
 }
 
-__device__ __forceinline__ int seg_find(volatile int32_t* parent, int x) {
-  int p;
-  while ((p = parent[x]) != x) x = p;
-  return x;
-}
-
-__device__ void seg_merge(int32_t* parent, int x, int y) {
-  bool done;
-  do {
-    x = seg_find(parent, x);
-    y = seg_find(parent, y);
-    if (x < y) {
-      const int old = atomicMin(&parent[y], x);
-      done = old == y;
-      y = old;
-    } else if (y < x) {
-      const int old = atomicMin(&parent[x], y);
-      done = old == x;
-      x = old;
-    } else {
-      done = true;
-    }
-  } while (!done);
-}
-
 __global__ void seg_union_kernel(const float2* __restrict__ fT, int A, int B, float tresh, int32_t* parent) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= A * B) return;
   if (parent[s] < 0) return;
   const float2 f = fT[s];
   const int a = s % A, b = s / A;
-  if (a + 1 < A && parent[s + 1] >= 0 && seg_near(f, fT[s + 1], tresh)) seg_merge(parent, s, s + 1);
-  if (b + 1 < B && parent[s + A] >= 0 && seg_near(f, fT[s + A], tresh)) seg_merge(parent, s, s + A);
+  if (a + 1 < A && parent[s + 1] >= 0 && seg_near(f, fT[s + 1], tresh)) uf_merge(parent, s, s + 1);
+  if (b + 1 < B && parent[s + A] >= 0 && seg_near(f, fT[s + A], tresh)) uf_merge(parent, s, s + A);
 }
 
 __global__ void seg_flatten_kernel(int n, int32_t* parent, int32_t* __restrict__ size) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   if (parent[s] < 0) return;
-  const int r = seg_find(parent, s);
+  const int r = uf_find(parent, s);
   parent[s] = r;   // a root keeps pointing at itself, so concurrent finds through s still end at r
   atomicAdd(&size[r], 1);
 }

@@ -211,6 +211,20 @@ def remove_small_segments(flow, tresh, min_segment_size, workspace=None):
     return flow
 
 
+def canny_edges(bgr, low=100, high=200, workspace=None):
+    """edge.canny_ivice (edge.py:19-35) without the file I/O: uint8 (H,W,3) device tensor -> float32 (H,W),
+    0.0 on an edge, 1.0 elsewhere."""
+    lib = _lib.load()
+    H, W, ch = bgr.shape
+    assert ch == 3
+    out = torch.empty((H, W), dtype=torch.float32, device=bgr.device)
+    if workspace is None:
+        workspace = torch.empty(int(lib.flowb200_edges_workspace_bytes(H, W)), dtype=torch.uint8, device=bgr.device)
+    _lib.check(lib.flowb200_canny_edges(_ptr(bgr, torch.uint8, "bgr"), H, W, int(low), int(high), _ptr(out),
+                                        _ptr(workspace), workspace.numel(), _stream()), "flowb200_canny_edges")
+    return out
+
+
 def epe(test_uvv, gt_uvv, abs_thresh=3.0):
     """visualization.errorImage (visualization.py:128-152): (mean EPE, outlier %, n_valid) over pixels valid in both."""
     lib = _lib.load()
