@@ -69,3 +69,24 @@ def test_canny_edges_bad_arguments():
     ws = torch.empty(16, dtype=torch.uint8, device="cuda")
     assert L.flowb200_canny_edges(img.data_ptr(), 8, 8, 100, 200, out.data_ptr(), ws.data_ptr(), 16, None) == lib.EWORKSPACE
     assert L.flowb200_canny_edges(None, 8, 8, 100, 200, out.data_ptr(), ws.data_ptr(), 16, None) == lib.EINVAL
+
+
+def test_spremi_za_epic_script(tmp_path):
+    """python spremiZaEpic.py <img1> <img2> <fwd.npy> <bwd.npy> <thr> canny (reference spremiZaEpic.py:1-27): the three
+    EpicFlow inputs equal the reference's own outputs; the EpicFlow binary is absent here, so the run ends the way the
+    reference's does without it (FileNotFoundError from subprocess.run, after all three files are written)."""
+    import subprocess
+    zc, ze = load_npz("consistency"), load_npz("edges")
+    np.save(tmp_path / "f.npy", zc["real_fwd"])
+    np.save(tmp_path / "b.npy", zc["real_bwd"])
+    assert cv2.imwrite(str(tmp_path / "k1.png"), ze["boxes_img"])
+    assert cv2.imwrite(str(tmp_path / "k2.png"), ze["noise_img"])
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "spremiZaEpic.py"), "k1.png", "k2.png", "f.npy", "b.npy",
+                        str(int(zc["real_thr"])), "canny"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "FileNotFoundError" in r.stderr, r.stderr[-2000:]
+    assert np.array_equal(np.load(tmp_path / "sparse_field.npy"), zc["real_out"])
+    with open(os.path.join(ROOT, "tests", "golden", "parovi_real.txt")) as f:
+        assert (tmp_path / "parovi.txt").read_text() == f.read()
+    e = np.fromfile(tmp_path / "ivice.bin", dtype=np.float32).reshape(ze["boxes_img"].shape[:2])
+    assert np.array_equal(e == 0, ze["boxes_edges"] == 1)
+    assert not (tmp_path / "epic.flo").exists()
