@@ -1,7 +1,7 @@
 """Recall of FLANN's randomized kd-forest against the exact per-cell search (north star: "reporting recall against
 FLANN").  pyflann (the reference's binding, daisy i flann.py:13) is not installable offline; cv2.flann_Index is the
 same FLANN code base (OpenCV's bundled fork) and is used with pyflann's defaults: kd-tree forest, 4 trees, 32 checks.
-CPU only; descriptors and the exact neighbours come from the oracle.  Usage: python tools/flann_recall.py [k]"""
+CPU only; descriptors and the exact neighbours come from the oracle.  Usage: python tests/tools/flann_recall.py [k]"""
 import importlib
 import json
 import os
@@ -9,7 +9,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import cv2  # noqa: E402
 from oracle import daisy as od  # noqa: E402

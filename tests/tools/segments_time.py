@@ -3,7 +3,7 @@
 result against the C oracle.  Writes gpurun_out/segments_time.json.  (The oracle is used as the checker only.)"""
 import importlib, json, os, sys, time
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 P = "lk-s-2022-estimacija-pokreta_b200"
