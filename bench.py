@@ -220,8 +220,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Mpix/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": 1, "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "H": p.H, "W": p.W, "K": p.maxnprop, "bcd_times": sweeps,
-                       "directions": directions},
+            "config": {"workload": args.workload, "H": p.H, "W": p.W, "K": p.maxnprop, "k_cell": p.k_cell,
+                       "n_gauss": p.n_gauss, "bcd_times": sweeps, "directions": directions,
+                       "parallelism": "CPU oracle on rank 0, all host threads; every step is the bounded sample "
+                                      "named in cpu_baseline.sample"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
