@@ -21,7 +21,7 @@ namespace flowb200 {
 namespace {
 
 struct SegLayout {
-  size_t fT, root, size, cchk, vis, queue, total;
+  size_t fT, root, size, cchk, vis, touch, queue, total;
 };
 
 SegLayout seg_layout(int A, int B) {
@@ -34,6 +34,7 @@ SegLayout seg_layout(int A, int B) {
   L.queue = o; o = align_up(o + n * sizeof(int32_t));
   L.cchk = o;  o = align_up(o + n);
   L.vis = o;   o = align_up(o + n);
+  L.touch = o; o = align_up(o + n);
   L.total = o;
   return L;
 }
@@ -75,6 +76,27 @@ __global__ void seg_flatten_kernel(int n, int32_t* parent, int32_t* __restrict__
   const int r = uf_find(parent, s);
   parent[s] = r;   // a root keeps pointing at itself, so concurrent finds through s still end at r
   atomicAdd(&size[r], 1);
+}
+
+// FLOWB200_SEG_PREFILTER=1: settle the seed events that cannot have an effect before the replay (segments_core.cuh).
+// Off by default: checked on the host (tests/test_segments_host.py) but not yet run or timed on a GPU.
+bool seg_prefilter_enabled() {
+  const char* e = getenv("FLOWB200_SEG_PREFILTER");
+  return e && e[0] == '1';
+}
+
+__global__ void seg_prefilter_invalid_kernel(SegState S) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S.A * S.B) return;
+  if (S.root[s] >= 0) return;
+  if (!seg_invalid_touches(S, s)) S.root[s] = kSegInvalidChecked;
+}
+
+__global__ void seg_prefilter_component_kernel(SegState S) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S.A * S.B) return;
+  if (S.root[s] != s) return;
+  if (seg_component_inert(S, s)) S.cchk[s] = 1;
 }
 
 // kWide = 1: 32 pixels of the column per step.  kWide = 4: 128 pixels per step, their state loads in flight together;
@@ -148,6 +170,7 @@ extern "C" int flowb200_remove_small_segments(float* flow, int A, int B, float t
   S.size = reinterpret_cast<const int32_t*>(ws + L.size);
   S.cchk = reinterpret_cast<uint8_t*>(ws + L.cchk);
   S.vis = reinterpret_cast<uint8_t*>(ws + L.vis);
+  S.touch = reinterpret_cast<uint8_t*>(ws + L.touch);
   S.queue = reinterpret_cast<int32_t*>(ws + L.queue);
   S.flow = flow;
   float2* fT = reinterpret_cast<float2*>(ws + L.fT);
@@ -157,6 +180,12 @@ extern "C" int flowb200_remove_small_segments(float* flow, int A, int B, float t
   seg_init_kernel<<<G, T, 0, stream>>>(flow, A, B, fT, root, size, reinterpret_cast<uint8_t*>(ws + L.cchk), S.vis);
   seg_union_kernel<<<G, T, 0, stream>>>(fT, A, B, tresh, root);
   seg_flatten_kernel<<<G, T, 0, stream>>>(n, root, size);
+  if (seg_prefilter_enabled()) {
+    FB_CUDA_CHECK(cudaMemsetAsync(S.touch, 0, (size_t)n, stream));
+    seg_prefilter_invalid_kernel<<<G, T, 0, stream>>>(S);
+    seg_prefilter_component_kernel<<<G, T, 0, stream>>>(S);
+    FB_LAUNCH_CHECK_N(2);
+  }
   if (seg_scan_width() == 1) {
     seg_replay_kernel<1><<<1, 32, 0, stream>>>(S);
   } else {

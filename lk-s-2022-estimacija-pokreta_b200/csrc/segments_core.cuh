@@ -41,6 +41,7 @@ struct SegState {
   const int32_t* size;    // pixels per component, at the root
   volatile uint8_t* cchk; // component already taken by a flood fill (at the root)
   uint8_t* vis;           // pixel already appended by the breadth-first replay of a removed segment
+  uint8_t* touch;         // prefilter: component has a near invalid 4-neighbour (at the root)
   int32_t* queue;         // A*B scan indices
   float* flow;            // the caller's field: valid flags are cleared here
 };
@@ -60,6 +61,32 @@ SEG_HD void seg_neighbours(const SegState& S, int s, int nb[4]) {
   nb[1] = a + 1 < S.A ? s + 1 : -1;
   nb[2] = b > 0 ? s - S.A : -1;
   nb[3] = b + 1 < S.B ? s + S.A : -1;
+}
+
+// ---- optional prefilter: seed events that cannot have any effect are settled before the replay ----
+// An invalid pixel none of whose valid 4-neighbours is near can never absorb anything: its event only marks itself.
+// A component that no invalid pixel can absorb (no near invalid 4-neighbour) and that is not removable (one pixel, or
+// min_size and more) has an event that only sets its own flag, which nobody else ever reads.  Both are marked visited
+// up front; neither the order of the remaining events nor what they see changes.
+// Step 1, per invalid pixel s: flag the components it could absorb; returns whether there is any.
+SEG_HD bool seg_invalid_touches(const SegState& S, int s) {
+  int nb[4];
+  seg_neighbours(S, s, nb);
+  const float2 fs = S.fT[s];
+  bool any = false;
+  for (int t = 0; t < 4; ++t) {
+    if (nb[t] < 0) continue;
+    const int32_t r = S.root[nb[t]];
+    if (r < 0 || !seg_near(fs, S.fT[nb[t]], S.tresh)) continue;
+    S.touch[r] = 1;
+    any = true;
+  }
+  return any;
+}
+// Step 2 (after step 1 has finished everywhere), per component root r
+SEG_HD bool seg_component_inert(const SegState& S, int r) {
+  const int32_t n = S.size[r];
+  return !S.touch[r] && (n == 1 || n >= S.min_size);
 }
 
 // One seed event of the scan (:40-75) for the unvisited pixel `seed`.  Returns the column the scan continues in:

@@ -17,11 +17,11 @@ static int find_root(std::vector<int32_t>& p, int x) {
   return x;
 }
 
-extern "C" int seg_emul(float* flow, int A, int B, float tresh, int min_size) {
+extern "C" int seg_emul(float* flow, int A, int B, float tresh, int min_size, int prefilter) {
   const int n = A * B;
   std::vector<float2> fT(n);
   std::vector<int32_t> root(n), size(n, 0), queue(n);
-  std::vector<uint8_t> cchk(n, 0), vis(n, 0);
+  std::vector<uint8_t> cchk(n, 0), vis(n, 0), touch(n, 0);
   for (int s = 0; s < n; ++s) {
     const float* p = flow + ((size_t)(s % A) * B + s / A) * 3;
     fT[s].x = p[0];
@@ -46,7 +46,13 @@ extern "C" int seg_emul(float* flow, int A, int B, float tresh, int min_size) {
   SegState S;
   S.A = A; S.B = B; S.tresh = tresh; S.min_size = min_size;
   S.fT = fT.data(); S.root = root.data(); S.size = size.data(); S.cchk = cchk.data(); S.vis = vis.data();
-  S.queue = queue.data(); S.flow = flow;
+  S.queue = queue.data(); S.flow = flow; S.touch = touch.data();
+  if (prefilter) {   // seg_prefilter_invalid_kernel, then seg_prefilter_component_kernel
+    for (int s = 0; s < n; ++s)
+      if (root[s] < 0 && !seg_invalid_touches(S, s)) root[s] = kSegInvalidChecked;
+    for (int s = 0; s < n; ++s)
+      if (root[s] == s && seg_component_inert(S, s)) cchk[s] = 1;
+  }
   // seg_replay_kernel, one pixel per step instead of 32
   for (int bo = 0; bo < B; ++bo) {
     int b = bo;

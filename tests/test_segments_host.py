@@ -25,23 +25,26 @@ def emul(tmp_path_factory):
                     os.path.join(HERE, "seg_host_emul.cpp")], check=True)
     lib = C.CDLL(so)
 
-    def run(flow, tresh, ms):
+    def run(flow, tresh, ms, prefilter=0):
         f = np.array(flow, dtype=np.float32, copy=True)
-        assert lib.seg_emul(f.ctypes.data_as(C.c_void_p), f.shape[0], f.shape[1], C.c_float(tresh), int(ms)) == 0
+        assert lib.seg_emul(f.ctypes.data_as(C.c_void_p), f.shape[0], f.shape[1], C.c_float(tresh), int(ms),
+                            int(prefilter)) == 0
         return f
     return run
 
 
-def test_replay_logic_golden(emul):
+@pytest.mark.parametrize("prefilter", [0, 1])
+def test_replay_logic_golden(emul, prefilter):
     z = load_npz("segments")
     for i in range(int(z["n"])):
         f, (tresh, ms) = z[f"c{i}_in"], z[f"c{i}_par"]
-        out = emul(f, float(tresh), int(ms))
+        out = emul(f, float(tresh), int(ms), prefilter)
         assert np.array_equal(out[..., :2], f[..., :2])
         assert np.array_equal(out[..., 2], z[f"c{i}_valid_out"].astype(np.float32)), i
 
 
-def test_replay_logic_vs_oracle_random(emul):
+@pytest.mark.parametrize("prefilter", [0, 1])
+def test_replay_logic_vs_oracle_random(emul, prefilter):
     rng = np.random.default_rng(77)
     removed = 0
     for it in range(120):
@@ -52,5 +55,5 @@ def test_replay_logic_vs_oracle_random(emul):
         ms = [100, 10, 4, 2, 1000, 1 << 30][int(rng.integers(0, 6))]
         want, n = cport.remove_small_segments(f, tresh, ms, want_count=True)
         removed += n
-        assert np.array_equal(emul(f, tresh, ms), want), (it, kind, A, B, tresh, ms)
+        assert np.array_equal(emul(f, tresh, ms, prefilter), want), (it, kind, A, B, tresh, ms)
     assert removed > 1000
