@@ -335,6 +335,9 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--knn-mode", type=int, default=None)
     ap.add_argument("--bcd-mode", default="int32", choices=["int32", "fp64"])
+    ap.add_argument("--inflight", type=int, default=1,
+                    help="pairs of one rank processed concurrently per step (own stream, workspace and host thread "
+                         "each; pairs are independent, README.md:40).  1 = one pair after the other (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
     args = ap.parse_args()
@@ -362,14 +365,52 @@ def main():
 
     # a few distinct synthetic pairs per rank, cycled (the per-step working set, ~GBs of proposals, is far
     # larger than L2, so steps do not warm each other)
-    npairs = 2
+    inflight = max(1, args.inflight)
+    npairs = max(2, inflight)
     pairs = [synth.make_pair(p.H, p.W, 10 * rank + i) for i in range(npairs)]
     dev_pairs = [(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()) for a, b, _, _ in pairs]
     ws = ops.pair_workspace(p, "cuda", bcd_mode)
 
-    def step(i):
+    def step_one(i):
         g0, g1 = dev_pairs[i % npairs]
         return ops.flow_pair(g0, g1, p, sweeps, directions, seed=i, bcd_mode=bcd_mode, workspace=ws)
+
+    if inflight > 1:
+        # a step = `inflight` independent pairs, each on its own stream, workspace and host thread (the library keeps
+        # one auxiliary stream per host thread for the backward direction).  The side streams start after the
+        # current stream's position and the current stream waits for all of them, so CUDA events recorded on the
+        # current stream bracket the whole batch.
+        import threading
+        side = [torch.cuda.Stream() for _ in range(inflight)]
+        wss = [ws] + [ops.pair_workspace(p, "cuda", bcd_mode) for _ in range(inflight - 1)]
+
+        def step_batch(i):
+            cur = torch.cuda.current_stream()
+            start = torch.cuda.Event()
+            start.record(cur)
+            outs, errs = [None] * inflight, []
+
+            def work(j):
+                try:
+                    torch.cuda.set_device(local)
+                    side[j].wait_event(start)
+                    with torch.cuda.stream(side[j]):
+                        g0, g1 = dev_pairs[(i * inflight + j) % npairs]
+                        outs[j] = ops.flow_pair(g0, g1, p, sweeps, directions, seed=i * inflight + j,
+                                                bcd_mode=bcd_mode, workspace=wss[j])
+                except Exception as e:     # re-raised on the main thread below
+                    errs.append(e)
+            th = [threading.Thread(target=work, args=(j,)) for j in range(inflight)]
+            for t_ in th:
+                t_.start()
+            for t_ in th:
+                t_.join()
+            if errs:
+                raise errs[0]
+            for s_ in side:
+                cur.wait_stream(s_)
+            return outs[0]
+    step = step_batch if inflight > 1 else step_one
 
     def barrier():
         if world > 1:
@@ -397,7 +438,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    mpix = world * p.H * p.W / 1e6 / (ms_step / 1e3)
+    mpix = world * inflight * p.H * p.W / 1e6 / (ms_step / 1e3)
 
     # ---- e2e: host buffers through the C-ABI context, H2D + D2H inside the timed region
     ctx = L.flowb200_ctx_create(C.byref(cp))
@@ -474,10 +515,11 @@ def main():
         line = {"metric": METRIC, "value": mpix, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": W_,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32" if bcd_mode == lib.BCD_INT32 else "f64", "data": "synthetic",
-                "pairs_per_s": world / (ms_step / 1e3),
+                "pairs_per_s": world * inflight / (ms_step / 1e3),
                 "config": {"workload": args.workload, "H": p.H, "W": p.W, "K": p.maxnprop, "k_cell": p.k_cell,
                            "n_gauss": p.n_gauss, "bcd_times": sweeps, "directions": directions,
                            "knn_mode": knn_mode, "bcd_mode": args.bcd_mode, "parallelism": f"pairs x{world}",
+                           "pairs_in_flight_per_gpu": inflight,
                            "l2": "per-step working set (proposals+costs, >1 GB) exceeds L2; 2 pairs cycled"},
                 "e2e": {"value": e2e_mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * p.H * p.W * 3,
                         "d2h_bytes_per_step": p.H * p.W * 12},
