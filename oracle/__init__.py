@@ -15,6 +15,11 @@ Pinning status (see DESIGN.md "Oracle"):
     unmodified source executed in the build container by `oracle/ref_harness.py`
     (script: `tests/golden/make_golden.py`), and `tests/test_oracle_golden.py` checks the
     restatements against them bit for bit.
+  * removeSmallSegments (`flow_oracle.c: fo_remove_small_segments`) is PINNED by outputs of the
+    reference's own function (`tests/golden/make_golden_segments.py`, `tests/test_oracle_c.py`);
+    the Canny edge map (`oracle/edges.py`) is PINNED twice: step by step against cv2 itself (its
+    arithmetic is OpenCV's main module, installed here) and against outputs of the reference's own
+    `edge.canny_ivice` (`tests/golden/make_golden_edges.py`, `tests/test_oracle_edges.py`).
   * DAISY (third-party opencv-contrib `xfeatures2d::DAISY`, no version pinned by the reference,
     not installable offline) and FLANN (third-party `pyflann`, approximate and unseeded) are
     PARITY UNPINNED: the restatement in `oracle/daisy.py` follows the published algorithm

@@ -65,11 +65,16 @@ def test_product_never_imports_oracle():
                 # comments may mention oracle/ files as documentation; imports and paths in code may not
                 code = "\n".join(l for l in src.splitlines() if not l.lstrip().startswith(("//", "#", "*", "/*")))
                 assert not pat.search(code), f"{fn} references the oracle"
-    for script in ("daisy i flann.py", "bcd.py", "python bcd.py", "postprocessing.py"):
+    scripts = ["daisy i flann.py", "bcd.py", "python bcd.py", "postprocessing.py", "napravi_parove.py", "edge.py",
+               "spremiZaEpic.py"]
+    tools = os.path.join(ROOT, "tools")      # diagnostics that need the oracle live under tests/tools instead
+    for dirpath, _, files in os.walk(tools):
+        scripts += [os.path.relpath(os.path.join(dirpath, fn), ROOT) for fn in files if fn.endswith(".py")]
+    for script in scripts:
         path = os.path.join(ROOT, script)
-        if os.path.isfile(path):
-            with open(path) as f:
-                assert not re.search(r"^\s*(from|import)\s+oracle\b", f.read(), re.M), script
+        assert os.path.isfile(path), script
+        with open(path) as f:
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", f.read(), re.M), script
 
 
 def test_proposal_packing_round_trip():
