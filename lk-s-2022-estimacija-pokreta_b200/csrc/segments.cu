@@ -158,6 +158,7 @@ extern "C" int flowb200_remove_small_segments(float* flow, int A, int B, float t
   if (!workspace) return FLOWB200_EINVAL;
   const SegLayout L = seg_layout(A, B);
   if (workspace_bytes < L.total) return FLOWB200_EWORKSPACE;
+  if (min_segment_size <= 2) return FLOWB200_OK;   // 1 < count < min_segment_size (:73) has no solution
   char* ws = static_cast<char*>(workspace);
   const int n = A * B;
   SegState S;
