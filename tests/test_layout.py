@@ -2,6 +2,7 @@
 declares; the product package never touches oracle/; host-side contract helpers round-trip."""
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -123,3 +124,21 @@ def test_parovi_match_list_is_byte_identical(tmp_path):
     napravi_parove.parovi(str(tmp_path / "f.npy"), str(tmp_path / "p.txt"))
     with open(os.path.join(GOLDEN, "parovi_real.txt")) as f:
         assert (tmp_path / "p.txt").read_text() == f.read()
+
+
+@pytest.mark.parametrize("script,argv,exc", [
+    ("daisy i flann.py", [], "IndexError"),                      # sys.argv[1] (daisy i flann.py:16)
+    ("daisy i flann.py", ["x", "0", "1"], "ValueError"),         # int(sys.argv[1])
+    ("daisy i flann.py", ["3", "0", "1"], "TypeError"),          # cv2.imread -> None, cropped at :52
+    ("bcd.py", ["3", "0"], "IndexError"),                        # sys.argv[3] (python bcd.py:17)
+    ("python bcd.py", ["3", "0", "2"], "FileNotFoundError"),     # np.load of the stage-1 files (:73-81)
+    ("spremiZaEpic.py", ["a.png", "b.png"], "IndexError"),       # sys.argv[3] (spremiZaEpic.py:12)
+])
+def test_cli_errors_are_the_references(tmp_path, script, argv, exc):
+    """SURVEY 8(b) 'Errors': the drop-in scripts fail the way the reference's do on bad arguments and missing inputs
+    (all of it happens before any GPU work, so it is checked here without one)."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, script)] + argv, cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode != 0
+    assert exc in r.stderr.strip().splitlines()[-1], r.stderr[-1500:]
