@@ -6,6 +6,7 @@ import importlib
 import json
 import os
 import sys
+import time
 
 import numpy as np
 
@@ -27,20 +28,32 @@ def main():
     cd2 = cell_descriptors(d2, p)
     rng = np.random.default_rng(0)
     hits = top1 = total = 0
+    t_build = t_search = 0.0
     for cell in range(p.ncellx * p.ncelly):
         tgt = np.ascontiguousarray(cd2[cell])
+        t0 = time.perf_counter()
         index = cv2.flann_Index(tgt, dict(algorithm=1, trees=4))
+        t_build += time.perf_counter() - t0
         ys, xs = rng.integers(0, H, 400), rng.integers(0, W, 400)
         q = np.ascontiguousarray(d1[ys, xs])
         exact = knn_exact(q, tgt, k)
+        t0 = time.perf_counter()
         approx, _ = index.knnSearch(q, k, params=dict(checks=32))
+        t_search += time.perf_counter() - t0
         for a, e in zip(approx, exact):
             hits += len(set(a.tolist()) & set(e.tolist()))
             top1 += int(a[0] == e[0])
         total += len(q)
     out = {"k": k, "queries": total, "recall_at_k": hits / (total * k), "top1_agreement": top1 / total,
            "index": "cv2.flann_Index(algorithm=KDTREE, trees=4), checks=32", "cells": p.ncellx * p.ncelly,
-           "image": f"{W}x{H} synthetic pair 3"}
+           "image": f"{W}x{H} synthetic pair 3",
+           # SURVEY 8(d) baseline (3): the kd-forest itself on this host's CPU, one thread, batched queries (the
+           # reference issues them one by one through Python); extrapolated to one direction of 1024x436
+           # (238 cells, 9.34 M (pixel, cell) searches)
+           "flann_build_ms_per_cell": round(1e3 * t_build / (p.ncellx * p.ncelly), 3),
+           "flann_search_us_per_query": round(1e6 * t_search / total, 3),
+           "flann_extrapolated_s_per_direction_1024x436": round(238 * t_build / (p.ncellx * p.ncelly)
+                                                                + 9.34e6 * t_search / total, 2)}
     print(json.dumps(out))
 
 
