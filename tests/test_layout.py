@@ -142,3 +142,16 @@ def test_cli_errors_are_the_references(tmp_path, script, argv, exc):
                        text=True, timeout=300)
     assert r.returncode != 0
     assert exc in r.stderr.strip().splitlines()[-1], r.stderr[-1500:]
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/flowb200.h is the drop-in boundary: it must compile as C99 (no C++ or torch types in the signatures) and
+    declare exactly the symbols the ctypes table binds."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "flowb200.h"\nint main(void) { return 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    "-fsyntax-only", str(src)], check=True)
+    with open(os.path.join(ROOT, "include", "flowb200.h")) as f:
+        declared = set(re.findall(r"\b(flowb200_[a-z0-9_]+)\s*\(", f.read()))
+    assert declared == set(pkg("_lib").SYMBOLS), declared ^ set(pkg("_lib").SYMBOLS)
