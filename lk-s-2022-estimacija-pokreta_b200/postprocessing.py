@@ -65,10 +65,32 @@ def removeSmallSegments(flow, tresh, min_segment_size):
                "flowb200_remove_small_segments_host")
 
 
+def _match_shape(f1, f2, a0, a1, b0, b1):
+    """flow2 of another shape than flow1.  The reference indexes flow2[u2][v2] with 0 <= u2 < A, 0 <= v2 < B
+    (flow1's shape, :80, :87-90) by flow2's OWN shape: rows/columns beyond (A, B) are never read, and a target
+    beyond flow2's extent raises IndexError (:97).  The device call takes one shape, so flow2 is cropped / zero
+    padded to (A, B) here, after the same IndexError test."""
+    A, B = f1.shape[0], f1.shape[1]
+    A2, B2 = f2.shape[0], f2.shape[1]
+    if A2 < A or B2 < B:
+        r = f1[a0:a1, b0:b1]
+        with np.errstate(invalid="ignore", over="ignore"):
+            u2 = np.trunc(r[:, :, 0] + np.arange(a0, a1, dtype=np.float32)[:, None])
+            v2 = np.trunc(r[:, :, 1] + np.arange(b0, b1, dtype=np.float32)[None, :])
+        inside = (r[:, :, 2] > 0.5) & (u2 >= 0) & (v2 >= 0) & (u2 < A) & (v2 < B)
+        if np.any(inside & ((u2 >= A2) | (v2 >= B2))):
+            raise IndexError(f"flow2 of shape {f2.shape} is indexed out of bounds by flow1 of shape {f1.shape}")
+    out = np.zeros((A, B, 3), dtype=np.float32)
+    out[:min(A, A2), :min(B, B2)] = f2[:min(A, A2), :min(B, B2)]
+    return out
+
+
 def _check_region(flow1, flow2, a0, a1, b0, b1, tresh):
     f1 = _inplace_field(flow1, "flow1")
     f2 = np.ascontiguousarray(_field(flow2, "flow2"), dtype=np.float32)
     A, B = f1.shape[0], f1.shape[1]
+    if f2.shape[:2] != f1.shape[:2]:
+        f2 = _match_shape(f1, f2, a0, a1, b0, b1)
     if f2 is f1 or np.shares_memory(f1, f2):
         f2 = f2.copy()
     L = _lib.load()

@@ -126,3 +126,34 @@ def test_postprocessing_module_dropin(tmp_path):
         pp.consistencyCheck(f1.flow, f2.flow, f1.height, 0, 10)
     with pytest.raises(TypeError):
         pp.fowardBackwardConsistency(g1.flow.astype(np.float64), f2.flow, 10)
+
+
+def test_consistency_flow2_of_another_shape():
+    """flow2 larger than flow1 is indexed by its own shape (rows/columns beyond flow1's extent are never read); a
+    smaller flow2 raises IndexError as soon as a target lies beyond it (postprocessing.py:80-97, numpy indexing)."""
+    sys.path.insert(0, ROOT)
+    pp = importlib.import_module("postprocessing")
+    from oracle import consistency as ocons
+    rng = np.random.default_rng(11)
+    A, B = 33, 47
+    f1 = np.zeros((A, B, 3), np.float32)
+    f1[..., :2] = rng.integers(-4, 5, size=(A, B, 2))
+    f1[..., 2] = rng.random((A, B)) < 0.9
+    big = np.zeros((A + 5, B + 9, 3), np.float32)
+    big[..., :2] = rng.integers(-4, 5, size=(A + 5, B + 9, 2))
+    big[..., 2] = rng.random((A + 5, B + 9)) < 0.9
+    got = f1.copy()
+    pp.fowardBackwardConsistency(got, big, 3.0)
+    assert np.array_equal(got, ocons.forward_backward_consistency(f1, big[:A, :B], 3.0))
+    with pytest.raises(IndexError):
+        pp.fowardBackwardConsistency(f1.copy(), big[:A - 6, :B - 6].copy(), 3.0)
+    # a smaller flow2 that is never indexed beyond its extent works like the reference: the pixels that would
+    # point beyond it are invalid, and invalid pixels return before flow2 is touched (:84-85)
+    ok = f1.copy()
+    a2 = np.trunc(ok[..., 0] + np.arange(A, dtype=np.float32)[:, None])
+    b2 = np.trunc(ok[..., 1] + np.arange(B, dtype=np.float32)[None, :])
+    ok[(a2 >= A - 3) | (b2 >= B - 3), 2] = 0
+    small = big[:A - 3, :B - 3].copy()
+    got = ok.copy()
+    pp.fowardBackwardConsistency(got, small, 3.0)
+    assert np.array_equal(got, ocons.forward_backward_consistency(ok, np.pad(small, ((0, 3), (0, 3), (0, 0))), 3.0))
