@@ -346,6 +346,30 @@ def test_epe_metric_matches_error_image():
     assert ops.epe(dev(t * 0), dev(g * 0))[2] == 0
 
 
+def test_epe_metric_golden():
+    """flowb200_epe against visualization.errorImage itself (tests/golden/epe.npz, make_golden_extra.py)."""
+    ops = pkg("ops")
+    z = load_npz("epe")
+    for k in range(3):
+        mean, outl, n = ops.epe(dev(z[f"c{k}_test"]), dev(z[f"c{k}_gt"]))
+        assert n == int(z[f"c{k}_nvalid"])
+        assert abs(mean - float(z[f"c{k}_mean"])) <= 2e-6 * max(1.0, float(z[f"c{k}_mean"]))   # float64 vs float32 mean
+        assert abs(outl - float(z[f"c{k}_outliers"])) < 1e-9
+
+
+def test_pack_for_c_golden():
+    """pakovanjeZaC (daisy i flann.py:321-398): flowb200_ksets_pack + stage1.pack_for_c against the four arrays the
+    reference's own function wrote (tests/golden/zac.npz), inside the [:nprop[p], :nprop[q]] region."""
+    from test_oracle_golden import assert_zac_equal
+    ops, ioc, stage1 = pkg("ops"), pkg("io_contract"), pkg("stage1")
+    z = load_npz("zac")
+    H, W, _, _, _, K = (int(v) for v in z["meta"])
+    pvec = np.full((H, W, K), -1, np.int32)
+    pvec[...] = ioc.pack_proposals(z["proposals"].astype(np.int64))
+    packed = ops.ksets_pack(dev(pvec), dev(z["nprop"], torch.int32)).cpu().numpy()
+    assert_zac_equal(stage1.pack_for_c(packed, H, W), z)
+
+
 # ---------------------------------------------------------------- whole path
 def test_pipeline_matches_stagewise_and_oracle():
     """flow_pair (device resident) == the stages called one by one; EPE vs the oracle pipeline <= 0.01 px."""

@@ -62,3 +62,61 @@ def test_consistency_pipeline_outputs():
     for thr in (10, 2):
         out = ocons.post_processing(z["b0_flow02"], z["b1_flow02"], thr)
         assert np.array_equal(out, z[f"sparse_thr{thr}"])
+
+
+def zac_masks(nprop, H, W, K):
+    """For every entry of the four `pakovani za c` arrays (daisy i flann.py:321-398): the (pixel, neighbour) pair it
+    holds, as index arrays.  Returns a list of four (index tuple into the array, p_y, p_x, q_y, q_x)."""
+    out = []
+    ty, tx = np.meshgrid(np.arange(H - 1), np.arange(0, W, 2), indexing="ij")           # even columns, down
+    out.append(((tx // 2, ty), ty, tx, ty + 1, tx))
+    ty, tx = np.meshgrid(np.arange(0, H, 2), np.arange(W - 1), indexing="ij")           # even rows, right to left
+    out.append(((ty // 2, W - 2 - tx), ty, tx, ty, tx + 1))
+    ty, tx = np.meshgrid(np.arange(H - 1), np.arange(1, W, 2), indexing="ij")           # odd columns, up
+    out.append((((W - 1 - tx) // 2, H - 2 - ty), ty, tx, ty + 1, tx))
+    ty, tx = np.meshgrid(np.arange(1, H, 2), np.arange(W - 1), indexing="ij")           # odd rows, left to right
+    out.append((((H - 1 - ty) // 2, tx), ty, tx, ty, tx + 1))
+    return out
+
+
+def assert_zac_equal(got, z):
+    """got: the four arrays of pack_for_c; z: tests/golden/zac.npz.  Bits are compared inside [:nprop[p], :nprop[q]]
+    (the reference's scratch matrix keeps stale bits outside it in the last row / column loops, :366-393); entries
+    the reference never writes must be zero in both."""
+    H, W, _, _, _, K = (int(v) for v in z["meta"])
+    nprop = z["nprop"].astype(np.int64)
+    for i, (where, py, px, qy, qx) in enumerate(zac_masks(nprop, H, W, K)):
+        want, have = z[f"zac{i}"], got[i]
+        assert have.shape == want.shape and have.dtype == np.uint8
+        written = np.zeros(want.shape[:2], bool)
+        written[where] = True
+        assert not want[~written].any() and not have[~written].any()
+        wb = np.unpackbits(want[where], axis=-1)[..., :K * K].reshape(py.shape + (K, K))
+        hb = np.unpackbits(have[where], axis=-1)[..., :K * K].reshape(py.shape + (K, K))
+        l = np.arange(K)
+        mask = (l[None, None, :, None] < nprop[py, px][..., None, None]) & \
+               (l[None, None, None, :] < nprop[qy, qx][..., None, None])
+        assert np.array_equal(wb & mask, hb & mask), f"pakovani za c {i}"
+        assert not (hb & ~mask).any()
+
+
+def test_pack_for_c_contents():
+    """stage1.pack_for_c (host re-layout of the K-set bits) against the reference's own pakovanjeZaC output."""
+    from helpers import pkg
+    z = load_npz("zac")
+    H, W, cw, ch, _, K = (int(v) for v in z["meta"])
+    p = oprop.Params(H, W, cw, ch, maxnprop=K)
+    pk = oprop.pakovanje(z["proposals"].astype(np.int64), z["nprop"].astype(np.int64), p)
+    assert_zac_equal(pkg("stage1").pack_for_c(pk, H, W), z)
+
+
+def test_error_image_metric():
+    """oracle.epe.error_image against visualization.errorImage itself (exec'd by tests/golden/make_golden_extra.py)."""
+    from oracle import epe as oepe
+    z = load_npz("epe")
+    for k in range(3):
+        mean, outl, n = oepe.error_image(z[f"c{k}_test"], z[f"c{k}_gt"])
+        assert n == int(z[f"c{k}_nvalid"])
+        # the reference prints str(np.float32 mean): equal to float32 precision; the percentage is an exact ratio
+        assert np.float32(mean) == np.float32(z[f"c{k}_mean"]), (mean, z[f"c{k}_mean"])
+        assert abs(outl - float(z[f"c{k}_outliers"])) < 1e-9
