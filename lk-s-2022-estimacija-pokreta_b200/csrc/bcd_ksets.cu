@@ -4,25 +4,32 @@
 //
 //   kset_sort_kernel   per pixel: label indices (and vectors) ordered by the spatial-hash bucket of the flow vector
 //   kset_build_kernel  per (pixel, chain orientation): one RECORD = everything a chain step needs, contiguous (layout
-//                      at the kernel).  Only pairs with L1 < tpsi are stored, as uint16 entries (k << 4 | L1 << 13),
-//                      labels ordered by decreasing list length and entries in jagged-diagonal order.  Records are
-//                      carved from an arena with one atomic cursor; a 64-bit descriptor per record (offset | size)
-//                      is the only index.  All (pixel, orientation) pairs are independent, so this kernel is
-//                      throughput bound, unlike the chains.
-//   kset_chain_kernel  one CTA per chain, one thread per label position.  Thread 0 streams the chain's records into a
-//                      ring of shared-memory slots with bulk asynchronous copies (TMA engine, mbarrier completion)
+//                      at the kernel).  Only pairs with L1 < tpsi are stored, as uint16 entries (k << 3 | L1 << 13),
+//                      labels ordered by decreasing list length, every list padded to whole groups of four entries.
+//                      Records are carved from an arena with one atomic cursor; a 64-bit descriptor per record
+//                      (offset | size) is the only index.  All (pixel, orientation) pairs are independent, so this
+//                      kernel is throughput bound, unlike the chains.
+//   kset_chain32_kernel  one CTA per chain, one thread per label position.  Thread 0 streams the chain's records into
+//                      a ring of shared-memory slots with bulk asynchronous copies (TMA engine, mbarrier completion)
 //                      four steps ahead; a step is: wait for the slot, min over the label's entry list of
-//                      rep[k] + (L1 << S), add the unary term, publish the new key, one block barrier.
+//                      key[k] + (L1 << S), add the unary term, publish the new key, one block barrier.
+//   kset_chain_kernel  the same with 64-bit keys: runs only the chains the 32-bit kernel could not certify.
 //
-// Keys are 64 bit (dp << 32 | label): "smallest dp, lowest label on ties" (np.argmin, python bcd.py:155/:175/:234) is
-// one unsigned 64-bit minimum (see Key below).  32-bit keys relative to the running minimum were
-// tried first: because of quirk Q1 (the truncation candidate is ignored when S_l is not empty, :170-176) the spread of
-// dp over the labels of a pixel is not bounded, ~5 % of the row chains of the bench workload overflowed 22 bits and had
-// to be re-run, and a phase lasts as long as its slowest chain.
+// Keys.  "Smallest dp, lowest label on ties" (np.argmin, python bcd.py:155/:175/:234) is one unsigned minimum of
+// (dp << 9 | label).  In 32 bits that leaves 23 bits for dp, so the 32-bit kernel keeps dp RELATIVE to the block
+// minimum of two steps earlier (minima never decrease along a chain) and SATURATES: a key >= satkey (2^31) means "too
+// large to represent", and every candidate derived from it is >= satkey again.  Because of quirk Q1 (the truncation
+// candidate is ignored when S_l is not empty, :170-176) the spread of dp over the labels of a pixel is unbounded, so
+// saturated labels do occur -- but a key below satkey is exact (it is the minimum over candidates of which every one
+// below satkey is exact), its back-pointer is exact, and its predecessor is below satkey too.  Hence the whole
+// backtracked path is exact whenever the final minimum is below satkey; otherwise the chain is flagged and re-run by the
+// 64-bit kernel (dp << 32 | label, no saturation), launched right behind.  FLOWB200_KSET_SATBITS lowers satkey for
+// tests that want to see the fallback at work.
 //
-// A record that does not fit (arena exhausted, staging or slot too small, list longer than 127, data cost out of 16
+// A record that does not fit (arena exhausted, staging or slot too small, list longer than 124, data cost out of 16
 // bits) gets descriptor 0 and
 // its step is evaluated densely from pvec/cost inside the chain kernel, so any workspace size gives the exact result.
+// Precondition of the int32 modes: 0 <= m < 65536 for every used slot (the uint32 dp bound of make_plan assumes it).
 #include <algorithm>
 #include <type_traits>
 
@@ -96,17 +103,17 @@ kset_sort_kernel(const int32_t* __restrict__ pvec, const int32_t* __restrict__ n
 // ------------------------------------------------------------------------------------------------
 // build: one CTA (kBuildThreads threads) per record
 //
-// Record layout (16-byte aligned, at most one chain-kernel slot):
-//   [0,16)   uint32 n, nr (rounds = longest list), struct byte offset, entry byte offset
-//   [16,..)  uint16 roff[nr+1]: first entry of round r; round r holds entry r of every label whose list is longer
-//            than r.  Labels are stored in order of DECREASING list length, so these labels are positions
-//            0 .. cnt_r-1 and entry r of position t sits at roff[r] + t (jagged-diagonal storage): the chain
-//            kernel's lanes read consecutive uint16 and the lanes of a warp have (almost) equal trip counts.
-//   structs  n x {int32 vector; uint32 data cost (16) | original label (9) << 16 | list length (7) << 25}
-//   entries  uint16 (k << 4) | (L1 << 13): previous-pixel label k (original index) and L1(v_l, u_k) < tpsi
-//   (roff is stored in BYTES, i.e. doubled, so that the chain kernel adds it to a byte pointer)
+// Record layout (16-byte aligned, at most one chain-kernel slot).  Labels are stored in order of DECREASING list
+// length (position t = thread t of the chain kernel), so that the lanes of a warp have (almost) equal trip counts:
+//   [0,16)   uint32 n, number of entry groups, struct byte offset, entry byte offset
+//   [16,..)  uint16 goff[n, padded to 8]: first entry group of position t
+//   structs  n x {int32 vector; uint32 data cost (16) | original label (9) << 16 | entry groups (7) << 25}
+//   entries  groups of four uint16 (8 bytes, one shared-memory load): (k << 3) | (L1 << 13) = previous-pixel label k
+//            (original index; << 3 = byte offset of its key pair in the chain kernel) and L1(v_l, u_k) < tpsi; a list
+//            is padded to whole groups with kNullEntry, whose "key" is the infinity word behind the key array.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxList = 127;                  // list length field: 7 bits
+constexpr int kMaxList = 124;                  // 31 groups of four
+constexpr uint32_t kNullEntry = 0x1000u;       // key offset 4096: the word behind the keys of labels 0..511
 constexpr uint32_t kCostLimit16 = 1u << 16;    // data cost field: 16 bits
 constexpr int kStagePerLabel = 16;             // staging capacity of the build kernel: candidates per label of Kpad
 constexpr int kSlotPerLabel = 12;              // chain-kernel slot capacity: stored entries per label of Kpad
@@ -152,10 +159,10 @@ __device__ __forceinline__ Ranges lookup_ranges(const uint32_t* rng, int32_t v, 
 }
 
 // Shared memory of one build CTA (one record at a time):
-// rng u32[kHashSize] | hist u32[128] | start u32[128] | misc u32[16] | vq2 int2[Kpad] | roff u16[136] |
+// rng u32[kHashSize] | hist u32[128] | start u32[128] | gstart u32[128] | misc u32[16] | vq2 int2[Kpad] |
 // kq3, ln, so, rk, inv, cq u16[Kpad] | stage u16[kStagePerLabel * Kpad]
 __host__ __device__ inline size_t build_smem_bytes(int Kpad) {
-  return (size_t)kHashSize * 4 + 128 * 4 * 2 + 64 + (size_t)Kpad * 8 + 136 * 2 + (size_t)Kpad * 2 * 6 +
+  return (size_t)kHashSize * 4 + 128 * 4 * 3 + 64 + (size_t)Kpad * 8 + (size_t)Kpad * 2 * 6 +
          (size_t)kStagePerLabel * Kpad * 2;
 }
 
@@ -177,11 +184,11 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
   uint32_t* rng = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* hist = rng + kHashSize;
   uint32_t* start = hist + 128;
-  uint32_t* misc = start + 128;          // [0] staged entries, [1] failure flag, [2] nr, [3] ok, [4..5] arena offset,
+  uint32_t* gstart = start + 128;        // first entry group of the labels with list length m
+  uint32_t* misc = gstart + 128;         // [0] staged entries, [1] failure flag, [3] ok, [4..5] arena offset,
                                          // [6] struct offset, [7] entry offset
   int2* vq2 = reinterpret_cast<int2*>(misc + 16);
-  uint16_t* roff = reinterpret_cast<uint16_t*>(vq2 + Kpad);
-  uint16_t* kq3 = roff + 136;
+  uint16_t* kq3 = reinterpret_cast<uint16_t*>(vq2 + Kpad);
   uint16_t* ln = kq3 + Kpad;
   uint16_t* so = ln + Kpad;
   uint16_t* rk = so + Kpad;
@@ -223,7 +230,7 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
       for (int s = t; s < nq; s += kBuildThreads) {
         const int32_t v = svq[s];
         vq2[s] = make_int2(vec_dy(v), vec_dx(v));
-        kq3[s] = (uint16_t)((uint32_t)sq[s] << 4);
+        kq3[s] = (uint16_t)((uint32_t)sq[s] << 3);
         inv[s] = (uint16_t)bucket_key(v, bshift);
       }
     }
@@ -297,43 +304,37 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
     }
     __syncthreads();
 
-    // 4. labels in order of decreasing list length (warp 0): start[m] = number of labels with a longer list;
-    //    roff[r] = sum_{r' < r} (labels with list longer than r') = sum_{r' < r} start[r'];  arena allocation
+    // 4. labels in order of decreasing list length (warp 0): start[m] = number of labels with a longer list,
+    //    gstart[m] = number of entry groups those labels take (a list of m entries takes ceil(m / 4));  arena allocation
     if (t < 32) {
       bool ok = misc[1] == 0;
       const uint32_t h0 = hist[4 * lane], h1 = hist[4 * lane + 1], h2 = hist[4 * lane + 2], h3 = hist[4 * lane + 3];
       const uint32_t hs = h0 + h1 + h2 + h3;
-      uint32_t suf = hs;
+      const uint32_t gl = (uint32_t)lane + 1u;                      // groups of a list of 4*lane+1 .. 4*lane+4 entries
+      const uint32_t ws = h0 * (uint32_t)lane + (h1 + h2 + h3) * gl;  // groups of this lane's four bins (bin 4*lane: lane)
+      uint32_t suf = hs, sufw = ws;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        uint32_t u = __shfl_down_sync(0xffffffffu, suf, o);
-        if (lane + o < 32) suf += u;
+        const uint32_t u = __shfl_down_sync(0xffffffffu, suf, o), uw = __shfl_down_sync(0xffffffffu, sufw, o);
+        if (lane + o < 32) {
+          suf += u;
+          sufw += uw;
+        }
       }
+      const uint32_t total = __shfl_sync(0xffffffffu, sufw, 0);     // entry groups of the record
       const uint32_t s3 = suf - hs, s2 = s3 + h3, s1 = s2 + h2, s0_ = s1 + h1;   // start of bins 4*lane+3 .. 4*lane
       start[4 * lane] = s0_;
       start[4 * lane + 1] = s1;
       start[4 * lane + 2] = s2;
       start[4 * lane + 3] = s3;
-      const int top = h3 ? 4 * lane + 3 : h2 ? 4 * lane + 2 : h1 ? 4 * lane + 1 : h0 ? 4 * lane : 0;
-      const int nr = __reduce_max_sync(0xffffffffu, top);                        // longest list
-      const uint32_t ls = s0_ + s1 + s2 + s3;
-      uint32_t pre = ls;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t u = __shfl_up_sync(0xffffffffu, pre, o);
-        if (lane >= o) pre += u;
-      }
-      pre -= ls;
-      roff[4 * lane] = (uint16_t)pre;
-      roff[4 * lane + 1] = (uint16_t)(pre + s0_);
-      roff[4 * lane + 2] = (uint16_t)(pre + s0_ + s1);
-      roff[4 * lane + 3] = (uint16_t)(pre + s0_ + s1 + s2);
-      __syncwarp();
-      const uint32_t total = roff[nr];
-      const int ntab = ((nr + 1 + 3) & ~3) + 8;   // round offsets, zero padded (the chain kernel reads groups of four ahead)
-      const uint32_t so_b = (uint32_t)(kRecHeader + 2 * ntab);
+      const uint32_t g3 = sufw - ws, g2 = g3 + h3 * gl, g1 = g2 + h2 * gl, g0 = g1 + h1 * gl;
+      gstart[4 * lane] = g0;
+      gstart[4 * lane + 1] = g1;
+      gstart[4 * lane + 2] = g2;
+      gstart[4 * lane + 3] = g3;
+      const uint32_t so_b = (uint32_t)(kRecHeader + 2 * ((n + 7) & ~7));
       const uint32_t eo_b = so_b + 8u * (uint32_t)n;
-      const unsigned long long bytes = ((unsigned long long)eo_b + 2ull * total + 15ull) & ~15ull;
+      const unsigned long long bytes = ((unsigned long long)eo_b + 8ull * total + 15ull) & ~15ull;
       unsigned long long off = 0;
       ok = ok && bytes <= slot_bytes;
       if (ok) {
@@ -342,7 +343,6 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
         ok = off + bytes <= arena_bytes;
       }
       if (lane == 0) {
-        misc[2] = (uint32_t)nr;
         misc[3] = ok ? 1u : 0u;
         misc[4] = (uint32_t)off;
         misc[5] = (uint32_t)(off >> 32);
@@ -352,7 +352,7 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
         if (ok) {
           uint32_t* h = reinterpret_cast<uint32_t*>(arena + off);
           h[0] = (uint32_t)n;
-          h[1] = (uint32_t)nr;
+          h[1] = total;
           h[2] = so_b;
           h[3] = eo_b;
         }
@@ -365,19 +365,26 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
       for (int j = t; j < n; j += kBuildThreads) inv[start[ln[j]] + rk[j]] = (uint16_t)j;
       __syncthreads();
       // 6. write the record
-      const int nr = (int)misc[2];
       unsigned char* rec = arena + (((unsigned long long)misc[5] << 32) | misc[4]);
-      uint16_t* ro_g = reinterpret_cast<uint16_t*>(rec + kRecHeader);
-      const int ntab = ((nr + 1 + 3) & ~3) + 8;
-      for (int r = t; r < ntab; r += kBuildThreads) ro_g[r] = r <= nr ? (uint16_t)(2u * roff[r]) : (uint16_t)0;
+      uint16_t* go_g = reinterpret_cast<uint16_t*>(rec + kRecHeader);
       uint2* st = reinterpret_cast<uint2*>(rec + misc[6]);
-      uint16_t* ents = reinterpret_cast<uint16_t*>(rec + misc[7]);
+      uint2* ents = reinterpret_cast<uint2*>(rec + misc[7]);
       for (int pos = t; pos < n; pos += kBuildThreads) {
         const int j = inv[pos];
         const int len = ln[j];
+        const int ng = (len + 3) >> 2;
+        const uint32_t g0 = gstart[len] + (uint32_t)rk[j] * (uint32_t)ng;
         const uint16_t* src = stage + so[j];
-        st[pos] = make_uint2((uint32_t)vp[j], (uint32_t)cq[j] | ((uint32_t)j << 16) | ((uint32_t)len << 25));
-        for (int r = 0; r < len; ++r) ents[roff[r] + pos] = src[r];
+        st[pos] = make_uint2((uint32_t)vp[j], (uint32_t)cq[j] | ((uint32_t)j << 16) | ((uint32_t)ng << 25));
+        go_g[pos] = (uint16_t)g0;
+        for (int g = 0; g < ng; ++g) {
+          const int r = 4 * g;
+          const uint32_t e0 = src[r];
+          const uint32_t e1 = r + 1 < len ? (uint32_t)src[r + 1] : kNullEntry;
+          const uint32_t e2 = r + 2 < len ? (uint32_t)src[r + 2] : kNullEntry;
+          const uint32_t e3 = r + 3 < len ? (uint32_t)src[r + 3] : kNullEntry;
+          ents[g0 + g] = make_uint2(e0 | (e1 << 16), e2 | (e3 << 16));
+        }
       }
     }
     // 7. empty the bucket table (4 KB: two 16-byte stores per thread) and the per-record state for the next record
