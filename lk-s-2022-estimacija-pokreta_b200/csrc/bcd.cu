@@ -604,7 +604,7 @@ static size_t legacy_workspace_bytes(int H, int W, int K) {
 // (or tpsi > 8); the float64 modes always run the implementation in this file.
 static bool use_ksets(int tpsi, int cost_shift) {
   static const bool legacy = getenv("FLOWB200_BCD_LEGACY") != nullptr;
-  return !legacy && tpsi >= 1 && tpsi <= 8 && cost_shift >= 3;
+  return !legacy && tpsi >= 1 && tpsi <= 8 && cost_shift >= 4;
 }
 
 extern "C" size_t flowb200_bcd_workspace_bytes(int H, int W, int K) {

@@ -399,16 +399,14 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
 // ------------------------------------------------------------------------------------------------
 // chains
 // ------------------------------------------------------------------------------------------------
-// Keys are 64 bit: dp << 32 | label, so that "smallest dp, lowest label on ties" (np.argmin, python bcd.py:155/:175/
-// :234) is one unsigned minimum (two compares + two selects; fmin on the bit patterns was tried and is worse: sm_100
-// has no DMNMX, it compiles to DSETP.MIN + selects + NaN quieting).
+// 64-bit keys of the generic kernel: dp << 32 | label, so that "smallest dp, lowest label on ties" (np.argmin, python
+// bcd.py:155/:175/:234) is one unsigned minimum; never saturates (make_plan bounds dp below 2^32).  The 32-bit keys of
+// the main kernel are described in the header of this file.
 using Key = unsigned long long;
 constexpr Key kKeyInf = ~0ull;
-
 __device__ __forceinline__ Key make_key(uint32_t dp, uint32_t label) { return ((Key)dp << 32) | label; }
-__device__ __forceinline__ Key key_add(Key k, uint32_t d) { return k + ((Key)d << 32); }
-__device__ __forceinline__ uint32_t key_dp(Key k) { return (uint32_t)(k >> 32); }
 __device__ __forceinline__ uint32_t key_label(Key k) { return (uint32_t)k; }
+__device__ __forceinline__ Key key_scaled(uint32_t units, int shift) { return (Key)(units << shift) << 32; }
 __device__ __forceinline__ Key key_min(Key a, Key b) { return a < b ? a : b; }
 __device__ __forceinline__ Key warp_min_key(Key k) {
   const uint32_t hi = (uint32_t)(k >> 32), lo = (uint32_t)k;
@@ -416,6 +414,8 @@ __device__ __forceinline__ Key warp_min_key(Key k) {
   const uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
   return ((Key)mh << 32) | ml;
 }
+// byte offset of the key pair of the label an entry names, + the buffer select
+__device__ __forceinline__ uint32_t key_off64(uint32_t e, uint32_t par_off) { return ((e & 0x1FF8u) << 1) | par_off; }
 
 struct ChainArgs {
   const int32_t* pvec;
@@ -425,36 +425,76 @@ struct ChainArgs {
   uint16_t* bp;
   const unsigned long long* desc;
   const unsigned char* arena;
+  int32_t* flags;     // per chain of the launch: the 32-bit kernel sets 1 when it cannot certify its result
   int H, W, K, Kpad, phase, chain0, tpsi, shift, slot_shift;   // chain = chain0 + blockIdx.x; 1 << slot_shift slots
   uint32_t slot_bytes;
+  uint32_t satkey;    // 32-bit keys >= satkey are "too large to represent"
   double lamda;
 };
 
-constexpr int kRepOff = 48 + 2 * 16 * 8;   // byte offset of rep_s in the chain kernel's shared memory
-constexpr int kSlotSlack = 1024;   // masked lanes of the entry loop may read (and ignore) this far past a record
+constexpr int kMaxWarps = 16;   // T <= 512
 
 __host__ __device__ inline size_t chain_fixed_smem(int Kpad, int len) {
-  // mbar[4] | present[4] | wred[2][16] keys | rep[2 * Kpad] keys | oldvec[len] | vprev[Kpad]; slots follow, 128-aligned
-  return (kRepOff + 2 * (size_t)Kpad * 8 + 4 * (size_t)len + 4 * (size_t)Kpad + 127) & ~(size_t)127;
+  // oldvec int32[len] | vprev int32[Kpad] | path uint16[len]; the record slots follow, 128-aligned
+  return (4 * (size_t)len + 4 * (size_t)Kpad + 2 * (size_t)len + 127) & ~(size_t)127;
 }
 
+// backtrack (:238-253) through the back-pointers of the chain of this block, staged through shared memory (the record
+// slots, free by now) a segment of rows at a time; the labels are written once the whole path is known
+template <int T>
+__device__ __forceinline__ void backtrack(const ChainArgs& a, const ChainGeom& g, int lab, uint16_t* path,
+                                          unsigned char* slots, int S) {
+  const int t = threadIdx.x, Kpad = a.Kpad;
+  const int rows_cap = max(1, (int)(((size_t)S * a.slot_bytes) / ((size_t)Kpad * 2)));
+  uint16_t* seg = reinterpret_cast<uint16_t*>(slots);
+  const int vec_per_row = Kpad / 8;   // uint4 = 8 back-pointers
+  const uint16_t* bp_chain = a.bp + (size_t)blockIdx.x * g.len * Kpad;
+  for (int hi = g.len - 1; hi >= 1; hi -= rows_cap) {
+    const int lo = max(1, hi - rows_cap + 1);
+    const int nrow = hi - lo + 1;
+    const uint4* src = reinterpret_cast<const uint4*>(bp_chain + (size_t)lo * Kpad);
+    uint4* dst = reinterpret_cast<uint4*>(seg);
+    for (int x = t; x < nrow * vec_per_row; x += T) dst[x] = src[x];
+    __syncthreads();
+    if (t == 0) {
+      for (int i = hi; i >= lo; --i) {
+        path[i] = (uint16_t)lab;
+        lab = seg[(size_t)(i - lo) * Kpad + lab];
+      }
+    }
+    __syncthreads();   // (uniform: lab is only meaningful in thread 0)
+  }
+  if (t == 0) path[0] = (uint16_t)lab;
+  __syncthreads();
+  for (int i = t; i < g.len; i += T) a.labels[(g.sy + i * g.ystep) * a.W + (g.sx + i * g.xstep)] = (int)path[i];
+}
+
+// The generic kernel (64-bit keys, steps whose record was not stored evaluated densely): runs only the chains the
+// 32-bit kernel flagged.
 template <typename CostT, int T>
-__device__ __forceinline__ void chain_body(const ChainArgs& a) {
+__device__ __forceinline__ void chain64_body(const ChainArgs& a) {
+  constexpr int NW = T / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  // rep_s[2 * k + b]: key of label k of the pixel visited at a step of parity b (the two buffers are interleaved so
+  // that an entry's byte offset and the buffer select combine in one logic operation); rep_s[1024 + b] stays
+  // infinite: it is where kNullEntry points
+  __shared__ __align__(16) Key rep_s[2 * 512 + 2];
+  __shared__ Key wred[2][kMaxWarps];           // warp minima of a step (infinite for warps without labels)
+  __shared__ uint32_t present_s[4];
+  __shared__ __align__(8) uint64_t mbar[4];
+  if (a.flags[blockIdx.x] == 0) return;   // (uniform) certified by the 32-bit kernel
+
   const ChainGeom g = chain_geom(a.phase, a.chain0 + (int)blockIdx.x, a.H, a.W);
-  const int t = threadIdx.x, lane = t & 31, wfirst = t & ~31;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int K = a.K, Kpad = a.Kpad, shift = a.shift, tpsi = a.tpsi;
   const int S = 1 << a.slot_shift, smask = S - 1;
   const int orient = a.phase & 1;
   const unsigned long long* dsc = a.desc + (size_t)orient * a.H * a.W;
   const CostT* cost = static_cast<const CostT*>(a.cost);
 
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
-  uint32_t* present_s = reinterpret_cast<uint32_t*>(smem_raw + 32);
-  Key* wred = reinterpret_cast<Key*>(smem_raw + 48);                          // [2][16] warp minima of a step
-  Key* rep_s = reinterpret_cast<Key*>(smem_raw + kRepOff);
-  int32_t* oldvec = reinterpret_cast<int32_t*>(smem_raw + kRepOff + 2 * (size_t)Kpad * 8);
+  int32_t* oldvec = reinterpret_cast<int32_t*>(smem_raw);
   int32_t* vprev = oldvec + g.len;
+  uint16_t* path = reinterpret_cast<uint16_t*>(vprev + Kpad);
   unsigned char* slots = smem_raw + chain_fixed_smem(Kpad, g.len);
 
   auto pixel = [&](int i) { return (g.sy + i * g.ystep) * a.W + (g.sx + i * g.xstep); };
@@ -463,6 +503,7 @@ __device__ __forceinline__ void chain_body(const ChainArgs& a) {
     const int p = pixel(i);
     oldvec[i] = a.pvec[(size_t)p * K + a.labels[p]];
   }
+  if (t < 2) rep_s[1024 + t] = kKeyInf;
   if (t == 0) {
     for (int s = 0; s < S; ++s) ptx::mbar_init(&mbar[s], 1);
     ptx::fence_barrier_init();
@@ -487,95 +528,71 @@ __device__ __forceinline__ void chain_body(const ChainArgs& a) {
     if (S < g.len) d_next = dsc[pixel(S)];
   }
 
-  // Block minimum of the previous step's keys (+ tpsi): the truncation candidate min_k(tpsi + dp_prev[k]), lowest k on
-  // ties (:152-157).  Every warp leaves the minimum of its keys in wred[parity][warp] (no atomics: a 64-bit shared
-  // atomicMin is a compare-and-swap loop that ten warps would contend on every step); only the labels with an empty
-  // K-set read them -- and labels are stored by decreasing list length, so those sit in the last warp or two.
-  const uint32_t tpsi_dp = (uint32_t)tpsi << shift;
-  int n_prev = 0;   // labels of the previous pixel (uniform)
-  auto trunc_of = [&](int step, int n_of_step) -> Key {
-    const Key* w = wred + (step & 1) * 16;
+  // Block minimum of a step's keys: every warp leaves the minimum of its keys in wred[parity][warp] (no atomics).  It
+  // serves the truncation candidate min_k(tpsi + dp_prev[k]), lowest k on ties (:152-157) -- read only by the labels
+  // with an empty K-set -- and the final label.
+  const Key tpsi_key = key_scaled((uint32_t)tpsi, shift);
+  auto block_min = [&](int step) -> Key {
+    const Key* w = wred[step & 1];
     Key m = kKeyInf;
-    for (int k = 0; k * 32 < n_of_step; ++k) m = key_min(m, w[k]);
-    return key_add(m, tpsi_dp);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) m = key_min(m, w[k]);
+    return m;
   };
   uint16_t* bp_row = a.bp + (size_t)blockIdx.x * g.len * Kpad;   // row of step i (advanced every step)
-  const uint32_t l1_scale = 1u << shift;
+  const unsigned char* rpb = reinterpret_cast<const unsigned char*>(rep_s);
 
   for (int i = 0; i < g.len; ++i, bp_row += Kpad) {
     const int slot = i & smask;
     ptx::mbar_wait(&mbar[slot], (uint32_t)(i >> a.slot_shift) & 1u);
     const uint32_t present = present_s[slot];
-    // rep_s[2 * k + b]: key of label k of the pixel visited at a step of parity b (the two buffers are interleaved so
-    // that an entry's byte offset and the buffer select combine in one logic operation)
     const uint32_t prv_off = (uint32_t)((i & 1) ^ 1) * (uint32_t)sizeof(Key);
-    const unsigned char* rpb = reinterpret_cast<const unsigned char*>(rep_s);
     Key* rc = rep_s + (i & 1);
     Key key = kKeyInf;
+    const int32_t ov_a = i + 1 < g.len ? oldvec[i + 1] : 0, ov_b = i > 0 ? oldvec[i - 1] : 0;
+    // data cost + the two side terms (sidepsi :84-88: the chain's own neighbours with their labels from before this
+    // call), in units of 2^-shift
+    auto unary = [&](int dy, int dx, uint32_t m) -> uint32_t {
+      uint32_t psi = 0;
+      if (i + 1 < g.len) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, ov_a));
+      if (i > 0) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, ov_b));
+      return m + (psi << shift);
+    };
+    // key of this step from the minimum `acc` over the previous step's candidates
+    auto next_key = [&](Key acc, uint32_t U, uint32_t orig) -> Key {
+      return acc - key_label(acc) + ((Key)U << 32) + orig;
+    };
     if (present) {
       const unsigned char* rec = slots + (size_t)slot * a.slot_bytes;
       const uint4 hdr = *reinterpret_cast<const uint4*>(rec);
       const int n = (int)hdr.x;
-      if (wfirst < n) {   // warps without labels only take part in the barrier
-        // unary side terms (sidepsi :84-88): the chain's own neighbours with their labels from before this call
-        const int32_t ov_a = i + 1 < g.len ? oldvec[i + 1] : 0, ov_b = i > 0 ? oldvec[i - 1] : 0;
-        if (t < n) {
-          const uint2 st = *reinterpret_cast<const uint2*>(rec + hdr.z + 8 * t);
-          const int32_t v = (int32_t)st.x;
-          const uint32_t pk = st.y;
-          const uint32_t orig = (pk >> 16) & 511u;
-          const int dy = vec_dy(v), dx = vec_dx(v);
-          uint32_t psi = 0;
-          if (i + 1 < g.len) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, ov_a));
-          if (i > 0) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, ov_b));
-          const uint32_t U = (pk & 0xFFFFu) + (psi << shift);
-          uint32_t dp = U;
-          if (i > 0) {
-            const int len = (int)(pk >> 25);
-            // Entry r of this label sits at roff[r] + 2*t (bytes).  Four rounds at a time (their loads are independent);
-            // rounds >= len are masked: what they read is stale but in bounds (the round-offset table is zero padded
-            // by 8 entries and a slot is followed by kSlotSlack bytes).
-            const unsigned char* roff = rec + kRecHeader;
-            const unsigned char* ents = rec + hdr.w + 2 * t;
-            auto load_e = [&](uint2 R, uint32_t (&e)[4]) {
-              e[0] = *reinterpret_cast<const uint16_t*>(ents + (R.x & 0xFFFFu));
-              e[1] = *reinterpret_cast<const uint16_t*>(ents + (R.x >> 16));
-              e[2] = *reinterpret_cast<const uint16_t*>(ents + (R.y & 0xFFFFu));
-              e[3] = *reinterpret_cast<const uint16_t*>(ents + (R.y >> 16));
-            };
-            Key acc0 = len ? kKeyInf : trunc_of(i - 1, n_prev);   // quirk Q1: truncation only when the K-set is empty
-            Key acc1 = kKeyInf, acc2 = kKeyInf, acc3 = kKeyInf;
-            uint2 R = *reinterpret_cast<const uint2*>(roff);
-            for (int r = 0; r < len; r += 4) {
-              uint32_t e[4];
-              load_e(R, e);
-              R = *reinterpret_cast<const uint2*>(roff + 2 * r + 8);   // next group's round offsets
-              Key c[4];
+      if (t < n) {
+        const uint2 st = *reinterpret_cast<const uint2*>(rec + hdr.z + 8 * t);
+        const uint32_t pk = st.y;
+        const uint32_t orig = (pk >> 16) & 511u;
+        const uint32_t U = unary(vec_dy((int32_t)st.x), vec_dx((int32_t)st.x), pk & 0xFFFFu);
+        if (i > 0) {
+          const int ng = (int)(pk >> 25);
+          const uint32_t g0 = *reinterpret_cast<const uint16_t*>(rec + kRecHeader + 2 * t);
+          const uint2* eg = reinterpret_cast<const uint2*>(rec + hdr.w) + g0;
+          // quirk Q1: the truncation candidate only when the K-set is empty
+          Key acc = ng ? kKeyInf : block_min(i - 1) + tpsi_key;
+          for (int gi = 0; gi < ng; ++gi) {
+            const uint2 w = eg[gi];
+            const uint32_t e[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {   // (k << 4) | buffer select = byte offset of rep_s[2 * k + b]
-                const uint2 kk = *reinterpret_cast<const uint2*>(rpb + ((e[j] & 0x1FF0u) | prv_off));
-                c[j] = make_key(kk.y + (e[j] >> 13) * l1_scale, kk.x);
-              }
-              acc0 = key_min(acc0, c[0]);
-              if (r + 1 < len) acc1 = key_min(acc1, c[1]);
-              if (r + 2 < len) acc2 = key_min(acc2, c[2]);
-              if (r + 3 < len) acc3 = key_min(acc3, c[3]);
-            }
-            const Key acc = key_min(key_min(acc0, acc1), key_min(acc2, acc3));
-            dp = key_dp(acc) + U;
-            bp_row[orig] = (uint16_t)key_label(acc);
+            for (int j = 0; j < 4; ++j)
+              acc = key_min(acc, *reinterpret_cast<const Key*>(rpb + key_off64(e[j], prv_off)) + key_scaled(e[j] >> 13, shift));
           }
-          key = make_key(dp, orig);
-          rc[2 * orig] = key;
+          bp_row[orig] = (uint16_t)key_label(acc);
+          key = next_key(acc, U, orig);
+        } else {
+          key = make_key(U, orig);
         }
-        // block minimum of (dp + tpsi, label) for the next step's truncation candidate (:152-157), lowest label on ties
-        const Key wmin = warp_min_key(key);
-        if (lane == 0) wred[(i & 1) * 16 + (t >> 5)] = wmin;
+        rc[2 * orig] = key;
       }
-      n_prev = n;
     } else {
       // dense step: the record was not stored; evaluate the K-set from the proposal arrays
-      const int32_t ov_a = i + 1 < g.len ? oldvec[i + 1] : 0, ov_b = i > 0 ? oldvec[i - 1] : 0;
       const int p = pixel(i);
       const int n = a.nprop[p];
       int nq = 0;
@@ -588,28 +605,26 @@ __device__ __forceinline__ void chain_body(const ChainArgs& a) {
       if (t < n) {
         const int32_t v = a.pvec[(size_t)p * K + t];
         const int dy = vec_dy(v), dx = vec_dx(v);
-        uint32_t psi = 0;
-        if (i + 1 < g.len) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, ov_a));
-        if (i > 0) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, ov_b));
-        const uint32_t U = (uint32_t)quant_cost<CostT>(cost[(size_t)p * K + t], a.lamda, shift) + (psi << shift);
-        uint32_t dp = U;
+        const uint32_t U = unary(dy, dx, (uint32_t)quant_cost<CostT>(cost[(size_t)p * K + t], a.lamda, shift));
         if (i > 0) {
           Key acc = kKeyInf;
           const Key* rp = rep_s + ((i & 1) ^ 1);
           for (int k = 0; k < nq; ++k) {
             const int l1 = l1_vec(dy, dx, vprev[k]);
-            if (l1 < tpsi) acc = key_min(acc, key_add(rp[2 * k], (uint32_t)l1 << shift));
+            if (l1 < tpsi) acc = key_min(acc, rp[2 * k] + key_scaled((uint32_t)l1, shift));
           }
-          if (acc == kKeyInf) acc = trunc_of(i - 1, n_prev);
-          dp = key_dp(acc) + U;
+          if (acc == kKeyInf) acc = block_min(i - 1) + tpsi_key;
           bp_row[t] = (uint16_t)key_label(acc);
+          key = next_key(acc, U, (uint32_t)t);
+        } else {
+          key = make_key(U, (uint32_t)t);
         }
-        key = make_key(dp, (uint32_t)t);
         rc[2 * t] = key;
       }
+    }
+    {
       const Key wmin = warp_min_key(key);
-      if (lane == 0 && (t & ~31) < n) wred[(i & 1) * 16 + (t >> 5)] = wmin;
-      n_prev = n;
+      if (lane == 0) wred[i & 1][warp] = wmin;
     }
     __syncthreads();
     if (t == 0 && i + S < g.len) {
@@ -618,38 +633,222 @@ __device__ __forceinline__ void chain_body(const ChainArgs& a) {
     }
   }
 
-  // final label: lowest-index argmin of dp_last (:231-237) = label field of the last block minimum; backtrack
-  // (:238-253) through the back-pointers, staged through shared memory a segment of rows at a time
-  int lab = (int)key_label(trunc_of(g.len - 1, n_prev));
-  const int rows_cap = max(1, (int)(((size_t)S * a.slot_bytes) / ((size_t)Kpad * 2)));
-  uint16_t* seg = reinterpret_cast<uint16_t*>(slots);
-  const int vec_per_row = Kpad / 8;   // uint4 = 8 back-pointers
-  const uint16_t* bp_chain = a.bp + (size_t)blockIdx.x * g.len * Kpad;
-  for (int hi = g.len - 1; hi >= 1; hi -= rows_cap) {
-    const int lo = max(1, hi - rows_cap + 1);
-    const int nrow = hi - lo + 1;
-    const uint4* src = reinterpret_cast<const uint4*>(bp_chain + (size_t)lo * Kpad);
-    uint4* dst = reinterpret_cast<uint4*>(seg);
-    for (int x = t; x < nrow * vec_per_row; x += T) dst[x] = src[x];
-    __syncthreads();
-    if (t == 0) {
-      for (int i = hi; i >= lo; --i) {
-        a.labels[pixel(i)] = lab;
-        lab = seg[(size_t)(i - lo) * Kpad + lab];
-      }
+  // final label: lowest-index argmin of dp_last (:231-237) = label field of the last block minimum
+  backtrack<T>(a, g, (int)key_label(block_min(g.len - 1)), path, slots, S);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The 32-bit chain kernel proper.  What bounds a chain is the LATENCY of one step (a chain is 436 or 1024 strictly
+// sequential steps and an SM holds only 1-4 chains), so the step is software pipelined: everything that does not
+// depend on the previous step's keys -- waiting for the record, header, label struct, unary term, the first three
+// entry groups -- is fetched for step i+1 in the same basic block as the key gathers of step i, so that the two
+// independent instruction streams hide each other's shared-memory latency.  Thread T-32 (a warp that has no labels
+// or the shortest lists) is the record producer.  Chains with a record that was not stored are left to the generic
+// 64-bit kernel (flags[chain] = 1), which evaluates such steps densely.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kNullWord = kNullEntry | (kNullEntry << 16);
+
+template <typename CostT, int T>
+__device__ __forceinline__ void chain32_body(const ChainArgs& a) {
+  constexpr int NW = T / 32;
+  constexpr uint32_t kInf = 0xFFFFFFFFu;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(16) uint32_t rep_s[2 * 512 + 2];   // [2 * k + parity] keys, [1024 + parity] = infinity (null entries)
+  __shared__ uint32_t wred[2][kMaxWarps];
+  __shared__ uint32_t delta_s[2];
+  __shared__ __align__(8) uint64_t mbar[4];
+  __shared__ int absent_s;
+
+  const ChainGeom g = chain_geom(a.phase, a.chain0 + (int)blockIdx.x, a.H, a.W);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int K = a.K, Kpad = a.Kpad, shift = a.shift, tpsi = a.tpsi;
+  const int S = 1 << a.slot_shift, smask = S - 1;
+  const unsigned long long* dsc = a.desc + (size_t)(a.phase & 1) * a.H * a.W;
+  const int len = g.len;
+
+  int32_t* oldvec = reinterpret_cast<int32_t*>(smem_raw);
+  uint16_t* path = reinterpret_cast<uint16_t*>(oldvec + len + Kpad);   // (same layout as the generic kernel)
+  unsigned char* slots = smem_raw + chain_fixed_smem(Kpad, len);
+  auto pixel = [&](int i) { return (g.sy + i * g.ystep) * a.W + (g.sx + i * g.xstep); };
+
+  if (t == 0) absent_s = 0;
+  __syncthreads();
+  {
+    bool absent = false;
+    for (int i = t; i < len; i += T) {
+      const int p = pixel(i);
+      oldvec[i] = a.pvec[(size_t)p * K + a.labels[p]];
+      absent |= (dsc[p] >> 40) == 0;
     }
-    __syncthreads();   // (uniform: lab is only meaningful in thread 0)
+    if (absent) absent_s = 1;
   }
-  if (t == 0) a.labels[pixel(0)] = lab;
+  if (t < 2) rep_s[1024 + t] = kInf;
+  if (t == 0) {
+    for (int s = 0; s < S; ++s) ptx::mbar_init(&mbar[s], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  if (absent_s) {   // (uniform)
+    if (t == 0) a.flags[blockIdx.x] = 1;
+    return;
+  }
+
+  const bool producer = t == T - 32;
+  unsigned long long d_next = 0;
+  auto issue = [&](int i, unsigned long long d) {
+    const int slot = i & smask;
+    const uint32_t bytes = (uint32_t)(d >> 40) << 4;
+    ptx::mbar_arrive_expect_tx(&mbar[slot], bytes);
+    ptx::bulk_load(slots + (size_t)slot * a.slot_bytes, a.arena + ((d & ((1ull << 40) - 1)) << 4), bytes, &mbar[slot]);
+  };
+  if (producer) {
+    for (int i = 0; i < S && i < len; ++i) issue(i, dsc[pixel(i)]);
+    if (S < len) d_next = dsc[pixel(S)];
+  }
+
+  const uint32_t tpsi_key = (uint32_t)tpsi << (shift + 9);
+  const uint32_t l1_mul = 1u << (shift - 4), l1_shr = (uint32_t)(20 - shift);   // (4 <= shift <= 14)
+  const uint32_t satkey = a.satkey;
+  const unsigned char* rpb = reinterpret_cast<const unsigned char*>(rep_s);
+  uint16_t* bp_row = a.bp + (size_t)blockIdx.x * len * Kpad + Kpad;   // row of step 1 (advanced every step)
+
+  // per-label state of a step, fetched one step ahead
+  struct Pre {
+    uint32_t U, orig, ng;
+    uint2 w0, w1, w2;
+    const uint2* eg;
+    int n;
+  };
+  auto prefetch = [&](int i) -> Pre {
+    Pre r;
+    const int slot = i & smask;
+    ptx::mbar_wait(&mbar[slot], (uint32_t)(i >> a.slot_shift) & 1u);
+    const unsigned char* rec = slots + (size_t)slot * a.slot_bytes;
+    const uint4 hdr = *reinterpret_cast<const uint4*>(rec);
+    r.n = (int)hdr.x;
+    const int tt = max(min(t, r.n - 1), 0);   // threads without a label redo the last one (and store nothing): no branches
+    const uint2 st = *reinterpret_cast<const uint2*>(rec + hdr.z + 8 * tt);
+    const uint32_t g0 = *reinterpret_cast<const uint16_t*>(rec + kRecHeader + 2 * tt);
+    r.eg = reinterpret_cast<const uint2*>(rec + hdr.w) + g0;
+    r.ng = st.y >> 25;
+    r.orig = (st.y >> 16) & 511u;
+    const uint2 e0 = r.eg[0], e1 = r.eg[1], e2 = r.eg[2];   // (in bounds: a slot is followed by slack)
+    r.w0 = r.ng > 0 ? e0 : make_uint2(kNullWord, kNullWord);
+    r.w1 = r.ng > 1 ? e1 : make_uint2(kNullWord, kNullWord);
+    r.w2 = r.ng > 2 ? e2 : make_uint2(kNullWord, kNullWord);
+    // data cost + the two side terms (sidepsi :84-88: the chain's own neighbours with their labels from before this
+    // call), in units of 2^-shift
+    const int dy = vec_dy((int32_t)st.x), dx = vec_dx((int32_t)st.x);
+    uint32_t psi = 0;
+    if (i + 1 < len) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, oldvec[i + 1]));
+    if (i > 0) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, oldvec[i - 1]));
+    r.U = (st.y & 0xFFFFu) + (psi << shift);
+    return r;
+  };
+  auto gather = [&](const uint2 w, uint32_t prv_off, uint32_t& m0, uint32_t& m1) {
+    uint32_t c0 = *reinterpret_cast<const uint32_t*>(rpb + ((w.x & 0x1FF8u) | prv_off));
+    uint32_t c1 = *reinterpret_cast<const uint32_t*>(rpb + (((w.x >> 16) & 0x1FF8u) | prv_off));
+    uint32_t c2 = *reinterpret_cast<const uint32_t*>(rpb + ((w.y & 0x1FF8u) | prv_off));
+    uint32_t c3 = *reinterpret_cast<const uint32_t*>(rpb + (((w.y >> 16) & 0x1FF8u) | prv_off));
+    c0 += (w.x & 0xE000u) * l1_mul;   // L1 << (shift + 9) straight from the packed words
+    c1 += (w.x & 0xE0000000u) >> l1_shr;
+    c2 += (w.y & 0xE000u) * l1_mul;
+    c3 += (w.y & 0xE0000000u) >> l1_shr;
+    m0 = min(m0, min(c0, c1));
+    m1 = min(m1, min(c2, c3));
+  };
+  auto publish = [&](int i, uint32_t key) {   // warp minimum of the step's keys; the block barrier
+    const uint32_t wmin = __reduce_min_sync(0xffffffffu, key);
+    if (lane == 0) wred[i & 1][warp] = wmin;
+    __syncthreads();
+    if (producer && i + S < len) {
+      issue(i + S, d_next);
+      if (i + S + 1 < len) d_next = dsc[pixel(i + S + 1)];
+    }
+  };
+  auto block_min = [&](int step) -> uint32_t {
+    const uint32_t* w = wred[step & 1];
+    uint32_t m = kInf;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) m = min(m, w[k]);
+    return m;
+  };
+
+  // step 0: dp_0 = unary (:118-120)
+  Pre cur = prefetch(0);
+  {
+    uint32_t key = kInf;
+    if (t < cur.n) {
+      key = (cur.U << 9) | cur.orig;
+      rep_s[2 * cur.orig] = key;
+    }
+    if (len > 1) {
+      const Pre nxt = prefetch(1);
+      publish(0, key);
+      cur = nxt;
+    } else {
+      publish(0, key);
+    }
+  }
+  // one step i >= 1; HasNext = there is a step i+1 to fetch ahead (all but the last step)
+  auto step = [&](int i, auto has_next) {
+    constexpr bool HasNext = decltype(has_next)::value;
+    const uint32_t prv_off = (uint32_t)((i & 1) ^ 1) << 2;
+    const uint32_t delta = i >= 2 ? delta_s[i & 1] : 0u;   // rebase of this step (see the header of this file)
+    // ---- the part that needs the previous step's keys
+    uint32_t acc0 = kInf, acc1 = kInf;
+    gather(cur.w0, prv_off, acc0, acc1);
+    gather(cur.w1, prv_off, acc0, acc1);
+    gather(cur.w2, prv_off, acc0, acc1);
+    // ---- rebase of step i+1 (warp 0): the block minimum of step i-1, expressed in step i's frame
+    if (HasNext && warp == 0) {
+      const uint32_t m = __reduce_min_sync(0xffffffffu, lane < NW ? wred[(i - 1) & 1][lane] : kInf);
+      if (lane == 0) delta_s[(i + 1) & 1] = (m & ~511u) - delta;
+    }
+    // ---- step i+1's label state (independent of the keys)
+    Pre nxt = cur;
+    if constexpr (HasNext) nxt = prefetch(i + 1);
+    // ---- lists longer than three groups, and the labels with an empty K-set (quirk Q1: the truncation candidate only
+    //      then; they sit in the last warps, labels being stored by decreasing list length)
+    for (uint32_t gi = 3; gi < cur.ng; ++gi) gather(cur.eg[gi], prv_off, acc0, acc1);
+    uint32_t acc = min(acc0, acc1);
+    if (cur.ng == 0) acc = block_min(i - 1) + tpsi_key;
+    // ---- new key: rebase, saturate (no wrap: acc < satkey <= 2^31, U < 2^18 + 2^(4 + shift))
+    const uint32_t v = (acc & ~511u) - delta + (cur.U << 9);
+    uint32_t key = kInf;
+    if (t < cur.n) {
+      key = (acc >= satkey ? satkey : min(v, satkey)) | cur.orig;
+      rep_s[2 * cur.orig + (i & 1)] = key;
+      bp_row[cur.orig] = (uint16_t)(acc & 511u);
+    }
+    publish(i, key);
+    cur = nxt;
+    bp_row += Kpad;
+  };
+  for (int i = 1; i + 1 < len; ++i) step(i, std::true_type{});
+  if (len > 1) step(len - 1, std::false_type{});
+
+  // final label: lowest-index argmin of dp_last (:231-237) = label field of the last block minimum; a saturated
+  // minimum cannot be certified: the 64-bit kernel redoes the chain
+  const uint32_t last = block_min(len - 1);
+  const bool bad = last >= satkey;   // (uniform)
+  if (t == 0) a.flags[blockIdx.x] = bad ? 1 : 0;
+  if (bad) return;
+  backtrack<T>(a, g, (int)(last & 511u), path, slots, S);
 }
 
 template <typename CostT, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) kset_chain_kernel(const ChainArgs a) {
-  chain_body<CostT, T>(a);
+  chain64_body<CostT, T>(a);
+}
+
+template <typename CostT, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) kset_chain32_kernel(const ChainArgs a) {
+  chain32_body<CostT, T>(a);
 }
 
 struct KsetLayout {
-  size_t bp, sorig, svec, desc, cursor, arena, arena_bytes, total;
+  size_t bp, sorig, svec, desc, cursor, flags, arena, arena_bytes, total;
   int Kst, Kpad;
 };
 
@@ -670,10 +869,11 @@ KsetLayout kset_layout(int H, int W, int K, size_t workspace_bytes) {
   L.svec = take(n * L.Kst * sizeof(int32_t));
   L.desc = take(2 * n * sizeof(unsigned long long));
   L.cursor = take(256);
+  L.flags = take((size_t)(((W > H ? W : H) + 1) / 2) * sizeof(int32_t));
   L.arena = off;
   if (workspace_bytes == 0) {
-    // default budget: header + round offsets + 8 B per label + ~8 entries per label, per record
-    L.arena_bytes = 2 * n * (size_t)(kRecHeader + 64 + 8 * K + 16 * K);
+    // default budget: header + 10 B per label + ~9 entries per label (whole groups of four), per record
+    L.arena_bytes = 2 * n * (size_t)(kRecHeader + 16 + 10 * K + 18 * K);
   } else {
     L.arena_bytes = workspace_bytes > off ? (workspace_bytes - off) & ~(size_t)15 : 0;
   }
@@ -697,11 +897,20 @@ static inline void owned_chains(int phase, int H, int W, int part, int nparts, i
 template <typename CostT>
 struct KsetPlan {
   KsetLayout L;
-  void (*kern)(const ChainArgs) = nullptr;
+  void (*kern32)(const ChainArgs) = nullptr;   // every chain, 32-bit saturating keys
+  void (*kern64)(const ChainArgs) = nullptr;   // the chains the first could not certify
   int T = 0, bshift = 0, slot_shift = 2;
-  uint32_t slot_bytes = 0;
+  uint32_t slot_bytes = 0, satkey = 0x80000000u;
   size_t smem = 0;
 };
+
+// satkey of the 32-bit chain kernel: 2^31 unless FLOWB200_KSET_SATBITS (10..31) asks for less, which sends more chains
+// to the 64-bit kernel (tests)
+static uint32_t satkey_from_env() {   // read at every call, so that a test can change it inside one process
+  const char* e = getenv("FLOWB200_KSET_SATBITS");
+  const int bits = e ? atoi(e) : 31;
+  return 1u << (bits < 10 ? 10 : bits > 31 ? 31 : bits);
+}
 
 template <typename CostT>
 static int make_plan(int H, int W, int K, int tpsi, int shift, size_t workspace_bytes, KsetPlan<CostT>* P) {
@@ -718,24 +927,32 @@ static int make_plan(int H, int W, int K, int tpsi, int shift, size_t workspace_
   // MB = chains per SM the shared-memory budget aims for.  The launch bound given to the compiler is at most 2: with
   // (320, 4) it allocated 48 registers and emitted 10 % MORE instructions than with (320, 2) (46 registers, which
   // still lets four CTAs share an SM) -- measured 1.03 -> 0.93 ms per column phase, 1.49 -> 1.31 ms per row phase.
-#define FB_KS_CASE(TT, MB) if (!P->kern && K <= TT) { P->kern = kset_chain_kernel<CostT, TT, (MB > 2 ? 2 : MB)>; P->T = TT; minb = MB; }
+#define FB_KS_CASE(TT, MB)                                          \
+  if (!P->kern32 && K <= TT) {                                      \
+    P->kern32 = kset_chain32_kernel<CostT, TT, (MB > 2 ? 2 : MB)>;  \
+    P->kern64 = kset_chain_kernel<CostT, TT, (MB > 2 ? 2 : MB)>;    \
+    P->T = TT;                                                      \
+    minb = MB;                                                      \
+  }
   FB_KS_CASE(64, 8) FB_KS_CASE(128, 6) FB_KS_CASE(192, 5) FB_KS_CASE(256, 4) FB_KS_CASE(320, 4)
   FB_KS_CASE(384, 3) FB_KS_CASE(512, 2)
 #undef FB_KS_CASE
-  if (!P->kern) return FLOWB200_EUNSUPPORTED;
+  if (!P->kern32) return FLOWB200_EUNSUPPORTED;
+  P->satkey = satkey_from_env();
   // ring of record slots: as many (<= 4) as keep `minb` chains per SM resident
   const int maxlen = H > W ? H : W;
-  // (masked lanes of the entry loop may also read a stale key up to 8 KB past the start of rep_s)
-  const size_t fixed = std::max(chain_fixed_smem(Kpad, maxlen) + kSlotSlack, (size_t)kRepOff + 8192 + 64);
-  // a slot holds header, round offsets, n structs and kSlotPerLabel entries per label; larger records go dense
+  const size_t fixed = chain_fixed_smem(Kpad, maxlen);
+  // a slot holds header, group offsets, n structs and kSlotPerLabel entries per label; larger records go dense
   P->slot_bytes =
-      (uint32_t)((kRecHeader + 288 + 8 * (size_t)Kpad + 2 * (size_t)kSlotPerLabel * Kpad + 127) & ~(size_t)127);
-  const size_t budget = (size_t)(227 * 1024) / minb - 1024;
+      (uint32_t)((kRecHeader + 2 * (size_t)Kpad + 8 * (size_t)Kpad + 2 * (size_t)kSlotPerLabel * Kpad + 127) & ~(size_t)127);
+  // static shared memory of the 64-bit kernel (keys 8.2 KB, minima: 9.4 KB) + the driver's 1 KB per CTA
+  const size_t budget = (size_t)(227 * 1024) / minb - 1024 - 9728;
   if (fixed + 4 * (size_t)P->slot_bytes > budget) P->slot_shift = 1;
   // long chains (large images): fewer resident chains rather than smaller slots
-  if (fixed + ((size_t)P->slot_bytes << P->slot_shift) > (size_t)227 * 1024) return FLOWB200_EUNSUPPORTED;
-  P->smem = fixed + ((size_t)P->slot_bytes << P->slot_shift);
-  FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem));
+  if (fixed + ((size_t)P->slot_bytes << P->slot_shift) + 64 + 9728 > (size_t)227 * 1024) return FLOWB200_EUNSUPPORTED;
+  P->smem = fixed + ((size_t)P->slot_bytes << P->slot_shift) + 64;   // slack: entry groups are fetched unconditionally
+  FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem));
+  FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem));
   return FLOWB200_OK;
 }
 
@@ -797,7 +1014,11 @@ int ksets_phase(const int32_t* pvec, const CostT* cost, const int32_t* nprop, in
   a.lamda = lamda;
   a.phase = phase;
   a.chain0 = c0;
-  P.kern<<<c1 - c0, P.T, P.smem, stream>>>(a);
+  a.flags = reinterpret_cast<int32_t*>(ws + L.flags);
+  a.satkey = P.satkey;
+  P.kern32<<<c1 - c0, P.T, P.smem, stream>>>(a);
+  FB_LAUNCH_CHECK();
+  P.kern64<<<c1 - c0, P.T, P.smem, stream>>>(a);   // blocks of certified chains return at once
   FB_LAUNCH_CHECK();
   return FLOWB200_OK;
 }

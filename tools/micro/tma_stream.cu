@@ -54,7 +54,19 @@ void run(const char* d, size_t region, int chunk, int nchunks, int ctas_per_sm, 
          cudaGetErrorString(cudaGetLastError()));
 }
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 1) {   // record-stream mode: chunks of the K-set record size from a region far larger than L2
+    const size_t total = 4096ull << 20;
+    char* d; cudaMalloc(&d, total); cudaMemset(d, 1, total);
+    const int chunk = atoi(argv[1]);
+    for (int cps : {1, 2, 3, 4}) {
+      run<1>(d, total, chunk, 2000, cps, 1);
+      run<2>(d, total, chunk, 2000, cps, 1);
+      run<4>(d, total, chunk, 2000, cps, 1);
+      run<8>(d, total, chunk, 2000, cps, 1);
+    }
+    return 0;
+  }
   const size_t total = 512ull << 20;
   char* d; cudaMalloc(&d, total); cudaMemset(d, 1, total);
   for (size_t region : {(size_t)64 << 20, (size_t)512 << 20}) {
