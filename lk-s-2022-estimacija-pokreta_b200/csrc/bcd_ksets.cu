@@ -110,10 +110,11 @@ kset_sort_kernel(const int32_t* __restrict__ pvec, const int32_t* __restrict__ n
 //   structs  n x {int32 vector; uint32 data cost (16) | original label (9) << 16 | entry groups (7) << 25}
 //   entries  groups of four uint16 (8 bytes, one shared-memory load): (k << 3) | (L1 << 13) = previous-pixel label k
 //            (original index; << 3 = byte offset of its key pair in the chain kernel) and L1(v_l, u_k) < tpsi; a list
-//            is padded to whole groups with kNullEntry, whose "key" is the infinity word behind the key array.
+//            is padded to whole groups with kNullEntry.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxList = 124;                  // 31 groups of four
-constexpr uint32_t kNullEntry = 0x1000u;       // key offset 4096: the word behind the keys of labels 0..511
+constexpr uint32_t kNullEntry = 0x1FF8u;       // bit 12 = "no entry"; its label field is 511, whose key slot the 32-bit
+                                               // chain kernel keeps infinite (it runs proposal sets of K <= 511 labels)
 constexpr uint32_t kCostLimit16 = 1u << 16;    // data cost field: 16 bits
 constexpr int kStagePerLabel = 16;             // staging capacity of the build kernel: candidates per label of Kpad
 constexpr int kSlotPerLabel = 12;              // chain-kernel slot capacity: stored entries per label of Kpad
@@ -415,7 +416,7 @@ __device__ __forceinline__ Key warp_min_key(Key k) {
   return ((Key)mh << 32) | ml;
 }
 // byte offset of the key pair of the label an entry names, + the buffer select
-__device__ __forceinline__ uint32_t key_off64(uint32_t e, uint32_t par_off) { return ((e & 0x1FF8u) << 1) | par_off; }
+__device__ __forceinline__ uint32_t key_off64(uint32_t e, uint32_t par_off) { return ((e & 0xFF8u) << 1) | par_off; }
 
 struct ChainArgs {
   const int32_t* pvec;
@@ -434,9 +435,20 @@ struct ChainArgs {
 
 constexpr int kMaxWarps = 16;   // T <= 512
 
+// a record slot of the chain kernels holds header, group offsets, n structs and kSlotPerLabel entries per label of
+// Kpad; larger records are not stored (their steps are evaluated densely)
+__host__ __device__ inline uint32_t kset_slot_bytes(int Kpad) {
+  return (uint32_t)((kRecHeader + 2 * (size_t)Kpad + 8 * (size_t)Kpad + 2 * (size_t)kSlotPerLabel * Kpad + 127) & ~(size_t)127);
+}
+// dynamic shared memory of the generic kernel: oldvec int32[len] | vprev int32[Kpad] | path uint16[len] | the record
+// slots, 128-aligned
 __host__ __device__ inline size_t chain_fixed_smem(int Kpad, int len) {
-  // oldvec int32[len] | vprev int32[Kpad] | path uint16[len]; the record slots follow, 128-aligned
   return (4 * (size_t)len + 4 * (size_t)Kpad + 2 * (size_t)len + 127) & ~(size_t)127;
+}
+// ... of the 32-bit kernel, behind the (run-time) pad that aligns it to 4 KB: keys 4 KB | oldvec int32[len] |
+// path uint16[len] | the record slots, 128-aligned
+__host__ __device__ inline size_t chain32_fixed_smem(int len) {
+  return (4096 + 4 * (size_t)len + 2 * (size_t)len + 127) & ~(size_t)127;
 }
 
 // backtrack (:238-253) through the back-pointers of the chain of this block, staged through shared memory (the record
@@ -476,9 +488,8 @@ __device__ __forceinline__ void chain64_body(const ChainArgs& a) {
   constexpr int NW = T / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // rep_s[2 * k + b]: key of label k of the pixel visited at a step of parity b (the two buffers are interleaved so
-  // that an entry's byte offset and the buffer select combine in one logic operation); rep_s[1024 + b] stays
-  // infinite: it is where kNullEntry points
-  __shared__ __align__(16) Key rep_s[2 * 512 + 2];
+  // that an entry's byte offset and the buffer select combine in one logic operation)
+  __shared__ __align__(16) Key rep_s[2 * 512];
   __shared__ Key wred[2][kMaxWarps];           // warp minima of a step (infinite for warps without labels)
   __shared__ uint32_t present_s[4];
   __shared__ __align__(8) uint64_t mbar[4];
@@ -503,7 +514,6 @@ __device__ __forceinline__ void chain64_body(const ChainArgs& a) {
     const int p = pixel(i);
     oldvec[i] = a.pvec[(size_t)p * K + a.labels[p]];
   }
-  if (t < 2) rep_s[1024 + t] = kKeyInf;
   if (t == 0) {
     for (int s = 0; s < S; ++s) ptx::mbar_init(&mbar[s], 1);
     ptx::fence_barrier_init();
@@ -582,7 +592,8 @@ __device__ __forceinline__ void chain64_body(const ChainArgs& a) {
             const uint32_t e[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              acc = key_min(acc, *reinterpret_cast<const Key*>(rpb + key_off64(e[j], prv_off)) + key_scaled(e[j] >> 13, shift));
+              if (!(e[j] & 0x1000u))   // (not a padding entry)
+                acc = key_min(acc, *reinterpret_cast<const Key*>(rpb + key_off64(e[j], prv_off)) + key_scaled(e[j] >> 13, shift));
           }
           bp_row[orig] = (uint16_t)key_label(acc);
           key = next_key(acc, U, orig);
@@ -638,37 +649,43 @@ __device__ __forceinline__ void chain64_body(const ChainArgs& a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// The 32-bit chain kernel proper.  What bounds a chain is the LATENCY of one step (a chain is 436 or 1024 strictly
-// sequential steps and an SM holds only 1-4 chains), so the step is software pipelined: everything that does not
-// depend on the previous step's keys -- waiting for the record, header, label struct, unary term, the first three
-// entry groups -- is fetched for step i+1 in the same basic block as the key gathers of step i, so that the two
-// independent instruction streams hide each other's shared-memory latency.  Thread T-32 (a warp that has no labels
-// or the shortest lists) is the record producer.  Chains with a record that was not stored are left to the generic
-// 64-bit kernel (flags[chain] = 1), which evaluates such steps densely.
+// The 32-bit chain kernel proper: one thread per label position, as few instructions per step as possible.  Measured
+// (ncu, profiles/): a chain step is bound by the NUMBER of warp instructions it issues -- an SM holds ~3 chains whose
+// warps each run one dependent instruction stream at ~7 cycles per instruction -- so what counts is: warps without
+// labels go straight to the barrier; the key array is 4 KB aligned, so that the shared-memory address of an entry's key
+// is ONE logic operation on the packed entry word (mask | base | buffer); the cost shift is a template parameter (12 is
+// what the scripts and the benchmark use; 0 = run time); the last warp, which has no labels or the shortest lists,
+// streams the records and reduces the block minimum for the rebase.  Chains with a record that was not stored are left
+// to the generic 64-bit kernel (flags[chain] = 1), which evaluates such steps densely.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kNullWord = kNullEntry | (kNullEntry << 16);
+constexpr int kKeyBytes = 4096;   // keys of labels 0..510 in two buffers; the slot of label 511 stays infinite (null entries)
 
-template <typename CostT, int T>
+template <typename CostT, int T, int SHIFT>
 __device__ __forceinline__ void chain32_body(const ChainArgs& a) {
   constexpr int NW = T / 32;
   constexpr uint32_t kInf = 0xFFFFFFFFu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(16) uint32_t rep_s[2 * 512 + 2];   // [2 * k + parity] keys, [1024 + parity] = infinity (null entries)
-  __shared__ uint32_t wred[2][kMaxWarps];
-  __shared__ uint32_t delta_s[2];
+  __shared__ uint32_t wred[2][kMaxWarps];   // warp minima of a step's keys (infinite for warps without labels)
+  __shared__ uint32_t delta_s[2];           // rebase of a step, by its parity
   __shared__ __align__(8) uint64_t mbar[4];
   __shared__ int absent_s;
 
   const ChainGeom g = chain_geom(a.phase, a.chain0 + (int)blockIdx.x, a.H, a.W);
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int K = a.K, Kpad = a.Kpad, shift = a.shift, tpsi = a.tpsi;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, wfirst = t & ~31;
+  const int K = a.K, Kpad = a.Kpad, tpsi = a.tpsi;
+  const int shift = SHIFT ? SHIFT : a.shift;
   const int S = 1 << a.slot_shift, smask = S - 1;
   const unsigned long long* dsc = a.desc + (size_t)(a.phase & 1) * a.H * a.W;
   const int len = g.len;
 
-  int32_t* oldvec = reinterpret_cast<int32_t*>(smem_raw);
-  uint16_t* path = reinterpret_cast<uint16_t*>(oldvec + len + Kpad);   // (same layout as the generic kernel)
-  unsigned char* slots = smem_raw + chain_fixed_smem(Kpad, len);
+  // dynamic shared memory: [pad] keys (4 KB aligned) | oldvec | path | record slots
+  const uint32_t dyn0 = ptx::smem_u32(smem_raw);
+  const uint32_t pad = (0u - dyn0) & (uint32_t)(kKeyBytes - 1);
+  uint32_t* rep_s = reinterpret_cast<uint32_t*>(smem_raw + pad);   // [2 * k + parity]
+  const uint32_t rep_u32 = dyn0 + pad;
+  int32_t* oldvec = reinterpret_cast<int32_t*>(smem_raw + pad + kKeyBytes);
+  uint16_t* path = reinterpret_cast<uint16_t*>(oldvec + len);
+  unsigned char* slots = smem_raw + pad + chain32_fixed_smem(len);
   auto pixel = [&](int i) { return (g.sy + i * g.ystep) * a.W + (g.sx + i * g.xstep); };
 
   if (t == 0) absent_s = 0;
@@ -680,9 +697,9 @@ __device__ __forceinline__ void chain32_body(const ChainArgs& a) {
       oldvec[i] = a.pvec[(size_t)p * K + a.labels[p]];
       absent |= (dsc[p] >> 40) == 0;
     }
-    if (absent) absent_s = 1;
+    if (absent || K > 511) absent_s = 1;   // (label 511's key slot is the padding entries' infinity)
   }
-  if (t < 2) rep_s[1024 + t] = kInf;
+  if (t < 2) rep_s[2 * 511 + t] = kInf;
   if (t == 0) {
     for (int s = 0; s < S; ++s) ptx::mbar_init(&mbar[s], 1);
     ptx::fence_barrier_init();
@@ -709,128 +726,86 @@ __device__ __forceinline__ void chain32_body(const ChainArgs& a) {
   const uint32_t tpsi_key = (uint32_t)tpsi << (shift + 9);
   const uint32_t l1_mul = 1u << (shift - 4), l1_shr = (uint32_t)(20 - shift);   // (4 <= shift <= 14)
   const uint32_t satkey = a.satkey;
-  const unsigned char* rpb = reinterpret_cast<const unsigned char*>(rep_s);
-  uint16_t* bp_row = a.bp + (size_t)blockIdx.x * len * Kpad + Kpad;   // row of step 1 (advanced every step)
+  uint16_t* bp_row = a.bp + (size_t)blockIdx.x * len * Kpad;   // row of step i (advanced every step)
+  const uint32_t mbar_u32 = ptx::smem_u32(mbar);
+  uint32_t delta_mine = 0;   // last warp: the rebase of the current step
 
-  // per-label state of a step, fetched one step ahead
-  struct Pre {
-    uint32_t U, orig, ng;
-    uint2 w0, w1, w2;
-    const uint2* eg;
-    int n;
-  };
-  auto prefetch = [&](int i) -> Pre {
-    Pre r;
+  for (int i = 0; i < len; ++i, bp_row += Kpad) {
     const int slot = i & smask;
-    ptx::mbar_wait(&mbar[slot], (uint32_t)(i >> a.slot_shift) & 1u);
+    ptx::mbar_wait_u32(mbar_u32 + 8u * (uint32_t)slot, (uint32_t)(i >> a.slot_shift) & 1u);
     const unsigned char* rec = slots + (size_t)slot * a.slot_bytes;
-    const uint4 hdr = *reinterpret_cast<const uint4*>(rec);
-    r.n = (int)hdr.x;
-    const int tt = max(min(t, r.n - 1), 0);   // threads without a label redo the last one (and store nothing): no branches
-    const uint2 st = *reinterpret_cast<const uint2*>(rec + hdr.z + 8 * tt);
-    const uint32_t g0 = *reinterpret_cast<const uint16_t*>(rec + kRecHeader + 2 * tt);
-    r.eg = reinterpret_cast<const uint2*>(rec + hdr.w) + g0;
-    r.ng = st.y >> 25;
-    r.orig = (st.y >> 16) & 511u;
-    const uint2 e0 = r.eg[0], e1 = r.eg[1], e2 = r.eg[2];   // (in bounds: a slot is followed by slack)
-    r.w0 = r.ng > 0 ? e0 : make_uint2(kNullWord, kNullWord);
-    r.w1 = r.ng > 1 ? e1 : make_uint2(kNullWord, kNullWord);
-    r.w2 = r.ng > 2 ? e2 : make_uint2(kNullWord, kNullWord);
-    // data cost + the two side terms (sidepsi :84-88: the chain's own neighbours with their labels from before this
-    // call), in units of 2^-shift
-    const int dy = vec_dy((int32_t)st.x), dx = vec_dx((int32_t)st.x);
-    uint32_t psi = 0;
-    if (i + 1 < len) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, oldvec[i + 1]));
-    if (i > 0) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, oldvec[i - 1]));
-    r.U = (st.y & 0xFFFFu) + (psi << shift);
-    return r;
-  };
-  auto gather = [&](const uint2 w, uint32_t prv_off, uint32_t& m0, uint32_t& m1) {
-    uint32_t c0 = *reinterpret_cast<const uint32_t*>(rpb + ((w.x & 0x1FF8u) | prv_off));
-    uint32_t c1 = *reinterpret_cast<const uint32_t*>(rpb + (((w.x >> 16) & 0x1FF8u) | prv_off));
-    uint32_t c2 = *reinterpret_cast<const uint32_t*>(rpb + ((w.y & 0x1FF8u) | prv_off));
-    uint32_t c3 = *reinterpret_cast<const uint32_t*>(rpb + (((w.y >> 16) & 0x1FF8u) | prv_off));
-    c0 += (w.x & 0xE000u) * l1_mul;   // L1 << (shift + 9) straight from the packed words
-    c1 += (w.x & 0xE0000000u) >> l1_shr;
-    c2 += (w.y & 0xE000u) * l1_mul;
-    c3 += (w.y & 0xE0000000u) >> l1_shr;
-    m0 = min(m0, min(c0, c1));
-    m1 = min(m1, min(c2, c3));
-  };
-  auto publish = [&](int i, uint32_t key) {   // warp minimum of the step's keys; the block barrier
-    const uint32_t wmin = __reduce_min_sync(0xffffffffu, key);
-    if (lane == 0) wred[i & 1][warp] = wmin;
+    const uint4 hdr = *reinterpret_cast<const uint4*>(rec);   // n, entry groups, struct offset, entry offset
+    const int n = (int)hdr.x;
+    uint32_t key = kInf;
+    if (t < n) {
+      const uint2 st = *reinterpret_cast<const uint2*>(rec + hdr.z + 8 * t);
+      const uint32_t orig = (st.y >> 16) & 511u;
+      // unary term: data cost + the two side terms (sidepsi :84-88: the chain's own neighbours with their labels from
+      // before this call), in units of 2^-shift
+      const int dy = vec_dy((int32_t)st.x), dx = vec_dx((int32_t)st.x);
+      uint32_t psi = 0;
+      if (i + 1 < len) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, oldvec[i + 1]));
+      if (i > 0) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, oldvec[i - 1]));
+      const uint32_t U = (st.y & 0xFFFFu) + (psi << shift);
+      if (i > 0) {
+        const uint32_t ng = st.y >> 25;
+        const uint32_t g0 = *reinterpret_cast<const uint16_t*>(rec + kRecHeader + 2 * t);
+        const uint2* eg = reinterpret_cast<const uint2*>(rec + hdr.w) + g0;
+        const uint32_t base = rep_u32 | ((uint32_t)((i & 1) ^ 1) << 2);   // previous step's buffer
+        uint32_t acc0 = kInf, acc1 = kInf;
+        for (uint32_t gi = 0; gi < ng; ++gi) {
+          const uint2 w = eg[gi];
+          uint32_t c0 = ptx::lds_u32((w.x & 0xFF8u) | base);
+          uint32_t c1 = ptx::lds_u32(((w.x >> 16) & 0xFF8u) | base);
+          uint32_t c2 = ptx::lds_u32((w.y & 0xFF8u) | base);
+          uint32_t c3 = ptx::lds_u32(((w.y >> 16) & 0xFF8u) | base);
+          c0 += (w.x & 0xE000u) * l1_mul;   // L1 << (shift + 9) straight from the packed words
+          c1 += (w.x & 0xE0000000u) >> l1_shr;
+          c2 += (w.y & 0xE000u) * l1_mul;
+          c3 += (w.y & 0xE0000000u) >> l1_shr;
+          acc0 = min(acc0, min(c0, c1));
+          acc1 = min(acc1, min(c2, c3));
+        }
+        uint32_t acc = min(acc0, acc1);
+        if (ng == 0) {   // quirk Q1: the truncation candidate only for an empty K-set (last warps: lists are sorted)
+          uint32_t m = kInf;
+#pragma unroll
+          for (int k = 0; k < NW; ++k) m = min(m, wred[(i - 1) & 1][k]);
+          acc = m + tpsi_key;
+        }
+        // rebase, saturate (no wrap: acc < satkey <= 2^31, U < 2^18 + 2^(4 + shift))
+        const uint32_t delta = delta_s[i & 1];
+        const uint32_t v = (acc & ~511u) - delta + (U << 9);
+        key = (acc >= satkey ? satkey : min(v, satkey)) | orig;
+        bp_row[orig] = (uint16_t)(acc & 511u);
+      } else {   // dp_0 = unary (:118-120)
+        key = (U << 9) | orig;
+      }
+      rep_s[2 * orig + (i & 1)] = key;
+    }
+    if (wfirst < n) key = __reduce_min_sync(0xffffffffu, key);   // (warp uniform) else: infinite
+    if (lane == 0) wred[i & 1][warp] = key;
+    if (warp == NW - 1) {   // rebase of step i+1: the block minimum of step i-1 in step i's frame (see the header)
+      uint32_t dn = 0;
+      if (i >= 1) {
+        const uint32_t m = __reduce_min_sync(0xffffffffu, lane < NW ? wred[(i - 1) & 1][lane] : kInf);
+        dn = (m & ~511u) - delta_mine;
+      }
+      if (lane == 0) delta_s[(i + 1) & 1] = dn;
+      delta_mine = dn;
+    }
     __syncthreads();
     if (producer && i + S < len) {
       issue(i + S, d_next);
       if (i + S + 1 < len) d_next = dsc[pixel(i + S + 1)];
     }
-  };
-  auto block_min = [&](int step) -> uint32_t {
-    const uint32_t* w = wred[step & 1];
-    uint32_t m = kInf;
-#pragma unroll
-    for (int k = 0; k < NW; ++k) m = min(m, w[k]);
-    return m;
-  };
-
-  // step 0: dp_0 = unary (:118-120)
-  Pre cur = prefetch(0);
-  {
-    uint32_t key = kInf;
-    if (t < cur.n) {
-      key = (cur.U << 9) | cur.orig;
-      rep_s[2 * cur.orig] = key;
-    }
-    if (len > 1) {
-      const Pre nxt = prefetch(1);
-      publish(0, key);
-      cur = nxt;
-    } else {
-      publish(0, key);
-    }
   }
-  // one step i >= 1; HasNext = there is a step i+1 to fetch ahead (all but the last step)
-  auto step = [&](int i, auto has_next) {
-    constexpr bool HasNext = decltype(has_next)::value;
-    const uint32_t prv_off = (uint32_t)((i & 1) ^ 1) << 2;
-    const uint32_t delta = i >= 2 ? delta_s[i & 1] : 0u;   // rebase of this step (see the header of this file)
-    // ---- the part that needs the previous step's keys
-    uint32_t acc0 = kInf, acc1 = kInf;
-    gather(cur.w0, prv_off, acc0, acc1);
-    gather(cur.w1, prv_off, acc0, acc1);
-    gather(cur.w2, prv_off, acc0, acc1);
-    // ---- rebase of step i+1 (warp 0): the block minimum of step i-1, expressed in step i's frame
-    if (HasNext && warp == 0) {
-      const uint32_t m = __reduce_min_sync(0xffffffffu, lane < NW ? wred[(i - 1) & 1][lane] : kInf);
-      if (lane == 0) delta_s[(i + 1) & 1] = (m & ~511u) - delta;
-    }
-    // ---- step i+1's label state (independent of the keys)
-    Pre nxt = cur;
-    if constexpr (HasNext) nxt = prefetch(i + 1);
-    // ---- lists longer than three groups, and the labels with an empty K-set (quirk Q1: the truncation candidate only
-    //      then; they sit in the last warps, labels being stored by decreasing list length)
-    for (uint32_t gi = 3; gi < cur.ng; ++gi) gather(cur.eg[gi], prv_off, acc0, acc1);
-    uint32_t acc = min(acc0, acc1);
-    if (cur.ng == 0) acc = block_min(i - 1) + tpsi_key;
-    // ---- new key: rebase, saturate (no wrap: acc < satkey <= 2^31, U < 2^18 + 2^(4 + shift))
-    const uint32_t v = (acc & ~511u) - delta + (cur.U << 9);
-    uint32_t key = kInf;
-    if (t < cur.n) {
-      key = (acc >= satkey ? satkey : min(v, satkey)) | cur.orig;
-      rep_s[2 * cur.orig + (i & 1)] = key;
-      bp_row[cur.orig] = (uint16_t)(acc & 511u);
-    }
-    publish(i, key);
-    cur = nxt;
-    bp_row += Kpad;
-  };
-  for (int i = 1; i + 1 < len; ++i) step(i, std::true_type{});
-  if (len > 1) step(len - 1, std::false_type{});
 
   // final label: lowest-index argmin of dp_last (:231-237) = label field of the last block minimum; a saturated
   // minimum cannot be certified: the 64-bit kernel redoes the chain
-  const uint32_t last = block_min(len - 1);
+  uint32_t last = kInf;
+#pragma unroll
+  for (int k = 0; k < NW; ++k) last = min(last, wred[(len - 1) & 1][k]);
   const bool bad = last >= satkey;   // (uniform)
   if (t == 0) a.flags[blockIdx.x] = bad ? 1 : 0;
   if (bad) return;
@@ -842,9 +817,9 @@ __global__ void __launch_bounds__(T, MINB) kset_chain_kernel(const ChainArgs a) 
   chain64_body<CostT, T>(a);
 }
 
-template <typename CostT, int T, int MINB>
+template <typename CostT, int T, int MINB, int SHIFT>
 __global__ void __launch_bounds__(T, MINB) kset_chain32_kernel(const ChainArgs a) {
-  chain32_body<CostT, T>(a);
+  chain32_body<CostT, T, SHIFT>(a);
 }
 
 struct KsetLayout {
@@ -901,7 +876,7 @@ struct KsetPlan {
   void (*kern64)(const ChainArgs) = nullptr;   // the chains the first could not certify
   int T = 0, bshift = 0, slot_shift = 2;
   uint32_t slot_bytes = 0, satkey = 0x80000000u;
-  size_t smem = 0;
+  size_t smem32 = 0, smem64 = 0;
 };
 
 // satkey of the 32-bit chain kernel: 2^31 unless FLOWB200_KSET_SATBITS (10..31) asks for less, which sends more chains
@@ -923,36 +898,35 @@ static int make_plan(int H, int W, int K, int tpsi, int shift, size_t workspace_
   if (workspace_bytes < P->L.arena) return FLOWB200_EWORKSPACE;
   const int Kpad = P->L.Kpad;
   while ((1 << P->bshift) < tpsi) ++P->bshift;
+  // one thread per label position; MB = chains per SM aimed at (registers and shared memory)
   int minb = 1;
-  // MB = chains per SM the shared-memory budget aims for.  The launch bound given to the compiler is at most 2: with
-  // (320, 4) it allocated 48 registers and emitted 10 % MORE instructions than with (320, 2) (46 registers, which
-  // still lets four CTAs share an SM) -- measured 1.03 -> 0.93 ms per column phase, 1.49 -> 1.31 ms per row phase.
-#define FB_KS_CASE(TT, MB)                                          \
-  if (!P->kern32 && K <= TT) {                                      \
-    P->kern32 = kset_chain32_kernel<CostT, TT, (MB > 2 ? 2 : MB)>;  \
-    P->kern64 = kset_chain_kernel<CostT, TT, (MB > 2 ? 2 : MB)>;    \
-    P->T = TT;                                                      \
-    minb = MB;                                                      \
+#define FB_KS_CASE(TT, MB)                                                                                   \
+  if (!P->kern32 && K <= TT) {                                                                               \
+    P->kern32 = shift == 12 ? kset_chain32_kernel<CostT, TT, (MB > 3 ? 3 : MB), 12>                          \
+                            : kset_chain32_kernel<CostT, TT, (MB > 3 ? 3 : MB), 0>;                          \
+    P->kern64 = kset_chain_kernel<CostT, TT, 1>;                                                             \
+    P->T = TT;                                                                                               \
+    minb = MB;                                                                                               \
   }
-  FB_KS_CASE(64, 8) FB_KS_CASE(128, 6) FB_KS_CASE(192, 5) FB_KS_CASE(256, 4) FB_KS_CASE(320, 4)
+  FB_KS_CASE(64, 8) FB_KS_CASE(128, 6) FB_KS_CASE(192, 5) FB_KS_CASE(256, 4) FB_KS_CASE(320, 3)
   FB_KS_CASE(384, 3) FB_KS_CASE(512, 2)
 #undef FB_KS_CASE
   if (!P->kern32) return FLOWB200_EUNSUPPORTED;
   P->satkey = satkey_from_env();
   // ring of record slots: as many (<= 4) as keep `minb` chains per SM resident
   const int maxlen = H > W ? H : W;
-  const size_t fixed = chain_fixed_smem(Kpad, maxlen);
-  // a slot holds header, group offsets, n structs and kSlotPerLabel entries per label; larger records go dense
-  P->slot_bytes =
-      (uint32_t)((kRecHeader + 2 * (size_t)Kpad + 8 * (size_t)Kpad + 2 * (size_t)kSlotPerLabel * Kpad + 127) & ~(size_t)127);
-  // static shared memory of the 64-bit kernel (keys 8.2 KB, minima: 9.4 KB) + the driver's 1 KB per CTA
-  const size_t budget = (size_t)(227 * 1024) / minb - 1024 - 9728;
-  if (fixed + 4 * (size_t)P->slot_bytes > budget) P->slot_shift = 1;
+  const size_t fixed32 = 4096 + chain32_fixed_smem(maxlen);   // (4096: worst case of the run-time alignment pad)
+  const size_t fixed64 = chain_fixed_smem(Kpad, maxlen);
+  P->slot_bytes = kset_slot_bytes(Kpad);
+  // + static shared memory (32-bit kernel 0.2 KB, 64-bit kernel 8.5 KB) + the driver's 1 KB per CTA
+  const size_t budget = (size_t)(227 * 1024) / minb - 1024 - 512;
+  if (fixed32 + 4 * (size_t)P->slot_bytes > budget) P->slot_shift = 1;
   // long chains (large images): fewer resident chains rather than smaller slots
-  if (fixed + ((size_t)P->slot_bytes << P->slot_shift) + 64 + 9728 > (size_t)227 * 1024) return FLOWB200_EUNSUPPORTED;
-  P->smem = fixed + ((size_t)P->slot_bytes << P->slot_shift) + 64;   // slack: entry groups are fetched unconditionally
-  FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem));
-  FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem));
+  P->smem32 = fixed32 + ((size_t)P->slot_bytes << P->slot_shift);
+  P->smem64 = fixed64 + ((size_t)P->slot_bytes << P->slot_shift);
+  if (P->smem32 + 1536 > (size_t)227 * 1024 || P->smem64 + 1024 + 8704 > (size_t)227 * 1024) return FLOWB200_EUNSUPPORTED;
+  FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem32));
+  FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem64));
   return FLOWB200_OK;
 }
 
@@ -1016,9 +990,9 @@ int ksets_phase(const int32_t* pvec, const CostT* cost, const int32_t* nprop, in
   a.chain0 = c0;
   a.flags = reinterpret_cast<int32_t*>(ws + L.flags);
   a.satkey = P.satkey;
-  P.kern32<<<c1 - c0, P.T, P.smem, stream>>>(a);
+  P.kern32<<<c1 - c0, P.T, P.smem32, stream>>>(a);
   FB_LAUNCH_CHECK();
-  P.kern64<<<c1 - c0, P.T, P.smem, stream>>>(a);   // blocks of certified chains return at once
+  P.kern64<<<c1 - c0, P.T, P.smem64, stream>>>(a);   // blocks of certified chains return at once
   FB_LAUNCH_CHECK();
   return FLOWB200_OK;
 }

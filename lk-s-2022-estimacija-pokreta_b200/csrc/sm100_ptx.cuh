@@ -50,6 +50,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// the same on a 32-bit shared-memory address
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP_U:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_U;\n\t"
+      "bra WAIT_LOOP_U;\n\t"
+      "DONE_U:\n\t"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// 32-bit load from a 32-bit shared-memory address.  volatile: not moved across the block barriers around it
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
 // same, but lets the hardware suspend the thread for up to `ns` nanoseconds per probe, so that a waiting
 // single-thread role does not steal issue slots from the warps doing the work
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
