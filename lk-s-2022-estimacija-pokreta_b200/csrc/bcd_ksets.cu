@@ -876,7 +876,7 @@ struct KsetPlan {
   void (*kern64)(const ChainArgs) = nullptr;   // the chains the first could not certify
   int T = 0, bshift = 0, slot_shift = 2;
   uint32_t slot_bytes = 0, satkey = 0x80000000u;
-  size_t smem32 = 0, smem64 = 0;
+  size_t smem32[2] = {0, 0}, smem64 = 0;   // smem32: by chain orientation (column chains are H long, row chains W)
 };
 
 // satkey of the 32-bit chain kernel: 2^31 unless FLOWB200_KSET_SATBITS (10..31) asks for less, which sends more chains
@@ -902,13 +902,13 @@ static int make_plan(int H, int W, int K, int tpsi, int shift, size_t workspace_
   int minb = 1;
 #define FB_KS_CASE(TT, MB)                                                                                   \
   if (!P->kern32 && K <= TT) {                                                                               \
-    P->kern32 = shift == 12 ? kset_chain32_kernel<CostT, TT, (MB > 3 ? 3 : MB), 12>                          \
-                            : kset_chain32_kernel<CostT, TT, (MB > 3 ? 3 : MB), 0>;                          \
+    P->kern32 = shift == 12 ? kset_chain32_kernel<CostT, TT, (MB > 4 ? 4 : MB), 12>                          \
+                            : kset_chain32_kernel<CostT, TT, (MB > 4 ? 4 : MB), 0>;                          \
     P->kern64 = kset_chain_kernel<CostT, TT, 1>;                                                             \
     P->T = TT;                                                                                               \
     minb = MB;                                                                                               \
   }
-  FB_KS_CASE(64, 8) FB_KS_CASE(128, 6) FB_KS_CASE(192, 5) FB_KS_CASE(256, 4) FB_KS_CASE(320, 3)
+  FB_KS_CASE(64, 8) FB_KS_CASE(128, 6) FB_KS_CASE(192, 5) FB_KS_CASE(256, 4) FB_KS_CASE(320, 4)
   FB_KS_CASE(384, 3) FB_KS_CASE(512, 2)
 #undef FB_KS_CASE
   if (!P->kern32) return FLOWB200_EUNSUPPORTED;
@@ -920,12 +920,15 @@ static int make_plan(int H, int W, int K, int tpsi, int shift, size_t workspace_
   P->slot_bytes = kset_slot_bytes(Kpad);
   // + static shared memory (32-bit kernel 0.2 KB, 64-bit kernel 8.5 KB) + the driver's 1 KB per CTA
   const size_t budget = (size_t)(227 * 1024) / minb - 1024 - 512;
-  if (fixed32 + 4 * (size_t)P->slot_bytes > budget) P->slot_shift = 1;
+  if (4096 + chain32_fixed_smem(H < W ? H : W) + 4 * (size_t)P->slot_bytes > budget) P->slot_shift = 1;
   // long chains (large images): fewer resident chains rather than smaller slots
-  P->smem32 = fixed32 + ((size_t)P->slot_bytes << P->slot_shift);
+  P->smem32[0] = 4096 + chain32_fixed_smem(H) + ((size_t)P->slot_bytes << P->slot_shift);
+  P->smem32[1] = 4096 + chain32_fixed_smem(W) + ((size_t)P->slot_bytes << P->slot_shift);
   P->smem64 = fixed64 + ((size_t)P->slot_bytes << P->slot_shift);
-  if (P->smem32 + 1536 > (size_t)227 * 1024 || P->smem64 + 1024 + 8704 > (size_t)227 * 1024) return FLOWB200_EUNSUPPORTED;
-  FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem32));
+  if (fixed32 + ((size_t)P->slot_bytes << P->slot_shift) + 1536 > (size_t)227 * 1024 ||
+      P->smem64 + 1024 + 8704 > (size_t)227 * 1024)
+    return FLOWB200_EUNSUPPORTED;
+  FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fixed32 + ((size_t)P->slot_bytes << P->slot_shift))));
   FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem64));
   return FLOWB200_OK;
 }
@@ -990,7 +993,7 @@ int ksets_phase(const int32_t* pvec, const CostT* cost, const int32_t* nprop, in
   a.chain0 = c0;
   a.flags = reinterpret_cast<int32_t*>(ws + L.flags);
   a.satkey = P.satkey;
-  P.kern32<<<c1 - c0, P.T, P.smem32, stream>>>(a);
+  P.kern32<<<c1 - c0, P.T, P.smem32[phase & 1], stream>>>(a);
   FB_LAUNCH_CHECK();
   P.kern64<<<c1 - c0, P.T, P.smem64, stream>>>(a);   // blocks of certified chains return at once
   FB_LAUNCH_CHECK();
