@@ -10,11 +10,10 @@
 //                     Targets of a cell are stored in a decimating permutation (pos -> idx = pos*s mod T) so that
 //                     every run of 32 columns is a spread-out sample of the cell.
 //  2. knn_select_kernel  tcgen05 GEMM (TMA -> smem -> tcgen05.mma -> TMEM, M=128 queries x N=128 targets per MMA
-//                     chunk, fp32 accumulate) with a fused streaming selection epilogue read back with tcgen05.ld:
-//                     every thread owns one query row, keeps the k smallest 32-column group minima (an upper bound
-//                     tau on the k-th smallest score) and appends every score <= tau + 2*eps to a shared-memory
-//                     list (compacted with the current tau when it fills); at the end of the cell the list is
-//                     filtered with the final tau.  eps bounds |a - exact score|
+//                     chunk, fp32 accumulate) with a fused selection epilogue read back with tcgen05.ld: every thread
+//                     owns one query row.  A cell's targets are streamed twice: pass 0 keeps the k smallest
+//                     32-column group minima (an upper bound tau on the k-th smallest score), pass 1 writes every
+//                     column with score <= tau + 2*eps to the candidate array.  eps bounds |a - exact score|
 //                     rigorously (fp16 rounding residual norms by Cauchy-Schwarz + fp32 accumulation slack), so the
 //                     surviving candidate set provably contains the exact k nearest neighbours (ties included).
 //  3. knn_rerank_kernel  exact float64 distances of the candidates (same arithmetic as the float64 brute force and
@@ -23,10 +22,9 @@
 //
 // One CTA = one 16x8-pixel query tile x one target cell at a time (persistent over a static work list), 6 warps:
 // warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue (one TMEM lane quadrant each).
-// Two CTAs are resident per SM (256 TMEM columns each) so one CTA's selection overlaps the other's MMAs.
-// Measured with the epilogue switched off (FLOWB200_KNN_EXPERIMENT=77/78): the TMA stream alone takes 1.8 ms and
-// TMA + tcgen05.mma 2.8 ms per direction (tensor pipe 53 % busy); the selection epilogue is what bounds the
-// kernel (~14 ms), at ~10 issue slots per score and two epilogue warps per scheduler.
+// Three CTAs are resident per SM (128 TMEM columns each) so that one CTA's selection overlaps the others' MMAs.
+// Measured in round 1 with the epilogue switched off: the TMA stream alone takes 1.8 ms and TMA + tcgen05.mma 2.8 ms
+// per direction (tensor pipe 53 % busy); the selection epilogue is what bounds the kernel.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
@@ -47,10 +45,9 @@ constexpr int kTilesPerItem = 1;                        // MMA tiles (x-adjacent
 constexpr int kChunkN = 128;       // targets per accumulator stage
 // Two passes over a cell's targets (the GEMM is recomputed; the tensor pipe is mostly idle anyway): pass 0 only
 // tracks the k smallest group minima (tau), pass 1 compares every score with the FINAL bound tau + 2 eps and
-// writes the few survivors straight to the candidate array.  No shared-memory lists, no compaction, ~3.6
-// instead of ~6.5 issue slots per score.  false = the single-pass streaming selection (kept for reference).
-constexpr bool kTwoPass = true;
-constexpr int kPasses = kTwoPass ? 2 : 1;
+// writes the few survivors straight to the candidate array.  No shared-memory lists, no compaction, ~3.6 issue slots
+// per score (a single-pass streaming selection with per-row lists in shared memory was built first: ~6.5).
+constexpr int kPasses = 2;
 #ifndef FLOWB200_KNN_CTAS
 #define FLOWB200_KNN_CTAS 3
 #endif
@@ -60,14 +57,12 @@ constexpr int kPasses = kTwoPass ? 2 : 1;
 // The two-pass selection needs no shared-memory lists, so more CTAs fit an SM: with ONE accumulator stage (128 TMEM
 // columns) three or four CTAs are resident and it is the other CTAs' epilogues, not a second accumulator stage of the
 // same CTA, that overlap a CTA's MMAs.
-constexpr int kCtasPerSM = kTwoPass ? FLOWB200_KNN_CTAS : 2 / kTilesPerItem;
-constexpr int kBStages = kTwoPass ? FLOWB200_KNN_BSTAGES : 2;
-constexpr int kAccStages = kTwoPass ? 1 : 2;
+constexpr int kCtasPerSM = FLOWB200_KNN_CTAS;
+constexpr int kBStages = FLOWB200_KNN_BSTAGES;
+constexpr int kAccStages = 1;
 constexpr int kTmemCols = kAccStages * kTilesPerItem * kChunkN;   // 128 (256 single-pass: two CTAs per SM)
 constexpr int kSlabBytes = kTileM * 32;                  // one k16 block of 128 rows: 4096 B
 constexpr int kTileBytes = kKB * kSlabBytes;             // 20480 B
-constexpr int kListCap = 96;       // (single-pass selection only) per-row candidate list in shared memory (compacted when > kListCap - 8)
-constexpr int kListBytes = kTwoPass ? 0 : kTilesPerItem * kListCap * kTileM * 4;
 constexpr int kCand = 32;          // candidates handed to the exact re-rank per (query, cell)
 constexpr int kSelThreads = 64 + 128 * kTilesPerItem;     // TMA warp, MMA warp, 4 epilogue warps per tile
 constexpr float kPadNorm = 60000.0f;   // n_hi of padding target rows: their score can never be selected
@@ -215,16 +210,6 @@ __device__ __forceinline__ void list_insert(float (&lst)[KC], float v) {
   }
 }
 
-// filter a row's shared-memory candidate list in place with the current bound; returns the new length
-__device__ __noinline__ int list_compact(uint32_t* lst, int cnt, float bound) {
-  int m = 0;
-  for (int e = 0; e < cnt; ++e) {
-    const uint32_t en = lst[e * kTileM];
-    if (__uint_as_float(en & 0xFFFFF800u) <= bound) lst[(m++) * kTileM] = en;
-  }
-  return m;
-}
-
 // decode a work item; returns false when the tile lies outside the cell's query band
 __device__ __forceinline__ bool decode_item(const KnnTcGeom& g, int item, int& cell, int& qx0, int& qy0, int& x1,
                                             int& y1) {
@@ -248,13 +233,12 @@ __global__ void __launch_bounds__(kSelThreads, kCtasPerSM)
 knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __restrict__ t16, KnnTcGeom g,
                   int n_items, const float2* __restrict__ qinfo, const int* __restrict__ cellinfo,
                   uint16_t* __restrict__ cand, uint8_t* __restrict__ cand_cnt, int32_t* __restrict__ counters,
-                  int counters_on, int experiment, float* __restrict__ dbg_scores) {
+                  int counters_on, float* __restrict__ dbg_scores) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                                                     // [tile][5 slabs]
   uint8_t* sB = smem + kTileBytes * kTilesPerItem;                                         // [stage][5 slabs]
-  uint32_t* list_e = reinterpret_cast<uint32_t*>(smem + kTileBytes * (kTilesPerItem + kBStages));   // [tile][kListCap][128]
-  SelSmem* ss = reinterpret_cast<SelSmem*>(reinterpret_cast<uint8_t*>(list_e) + kListBytes);
+  SelSmem* ss = reinterpret_cast<SelSmem*>(smem + kTileBytes * (kTilesPerItem + kBStages));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = g.Tpad / kChunkN;
@@ -287,14 +271,12 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __re
         int cell, qx0, qy0, x1, y1;
         if (!decode_item(g, item, cell, qx0, qy0, x1, y1)) continue;
         ptx::mbar_wait_backoff(&ss->a_empty, (it & 1) ^ 1, 2000);
-        if (experiment == 79) { ptx::mbar_arrive(&ss->a_full); } else {
         ptx::mbar_arrive_expect_tx(&ss->a_full, kTileBytes * kTilesPerItem);
 #pragma unroll
         for (int m = 0; m < kTilesPerItem; ++m)
 #pragma unroll
           for (int kb = 0; kb < kKB; ++kb)
             ptx::tma_load_3d(sA + m * kTileBytes + kb * kSlabBytes, &tmap_q, &ss->a_full, kb * 16, qx0 + m * kTileW, qy0);
-        }
         for (int cc = 0; cc < kPasses * nchunks; ++cc, ++bcount) {
           const int c = cc % nchunks;
           const uint32_t st = bcount % kBStages, ph = (bcount / kBStages) & 1;
@@ -324,13 +306,8 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __re
           const uint32_t st = bcount % kBStages, ph = (bcount / kBStages) & 1;
           const uint32_t acc = bcount % kAccStages, aph = (bcount / kAccStages) & 1;
           ptx::mbar_wait_backoff(&ss->b_full[st], ph, 100);
-          if (experiment != 80) ptx::mbar_wait_backoff(&ss->t_empty[acc], aph ^ 1, 100);
+          ptx::mbar_wait_backoff(&ss->t_empty[acc], aph ^ 1, 100);
           ptx::tc_fence_after();
-          if (experiment >= 78) {   // timing experiment: TMA streaming only, no MMA
-            ptx::mbar_arrive(&ss->b_empty[st]);
-            if (experiment != 80) ptx::mbar_arrive(&ss->t_full[acc]);
-            continue;
-          }
 #pragma unroll
           for (int m = 0; m < kTilesPerItem; ++m)
 #pragma unroll
@@ -348,7 +325,7 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __re
     }
   } else {
     // ===================== selection epilogue =====================
-    if constexpr (kTwoPass) {
+    {
       const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
       const int mt = (warp - 2) >> 2;              // which of the item's tiles this warp serves
       const int row = quad * 32 + lane;            // query row of the tile = TMEM lane
@@ -430,12 +407,6 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __re
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (acc * kTilesPerItem + mt) * kChunkN;
             const int cpos = c * kChunkN;
-            if (experiment >= 77) {   // timing experiment: TMA + MMA pipeline only
-              ptx::tc_fence_before();
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(&ss->t_empty[acc]);
-              continue;
-            }
             uint32_t r0[32], r1[32];
             ptx::tmem_ld_32x32(taddr, r0);
             ptx::tmem_ld_wait();
@@ -470,146 +441,7 @@ knn_select_kernel(const __grid_constant__ CUtensorMap tmap_q, const __half* __re
           if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 4), (unsigned long long)tot);
         }
       }
-    } else {
-    const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
-    const int mt = (warp - 2) >> 2;              // which of the item's tiles this warp serves
-    const int row = quad * 32 + lane;            // query row of the tile = TMEM lane
-    uint32_t* my_list = list_e + mt * kListCap * kTileM + row;   // candidate list of this row: [entry][row]
-    const uint32_t list_base = ptx::smem_u32(my_list);
-    uint32_t bcount = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      int cell, qx0, qy0, x1, y1;
-      if (!decode_item(g, item, cell, qx0, qy0, x1, y1)) continue;
-      const int px = qx0 + mt * kTileW + (row & (kTileW - 1)), py = qy0 + (row >> 4);
-      const bool valid = px < x1 && py < y1;
-      const int pix = valid ? py * g.W + px : 0;
-      // eps >= |a - exact score| for every target of the cell (see file header)
-      const float2 qi = qinfo[pix];
-      const float rt = __int_as_float(cellinfo[4 * cell + 0]), nt = __int_as_float(cellinfo[4 * cell + 1]);
-      const float nmax = __int_as_float(cellinfo[4 * cell + 2]);
-      const float eps = qi.x * nt + qi.y * rt + rt * (nt + rt) + 2.0e-5f * (qi.y * nt + nmax) + 1.0e-5f * nmax;
-      const float eps2 = 2.0f * up(eps);
-
-      float lst[KC];
-#pragma unroll
-      for (int j = 0; j < KC; ++j) lst[j] = CUDART_INF_F;
-      bool overflow = false;
-
-      // One group = 32 consecutive score columns of this row, already in registers.  List entries are the
-      // score with its 11 low mantissa bits replaced by the column position (scores are >= 0 up to rounding,
-      // so the truncated score is <= the score: later filters on the stored value keep a superset).
-      uint32_t waddr = list_base;               // shared address of the next free entry of this row
-      auto process = [&](const uint32_t (&r)[32], int pos0, bool first) {
-        if constexpr (DBG) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            dbg_scores[((size_t)(item * kTilesPerItem + mt) * kTileM + row) * g.Tpad + pos0 + j] = __uint_as_float(r[j]);
-        }
-        if (first) {   // first group of the cell: 16 pair minima (distinct elements) seed the list
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            list_insert<KC>(lst, fminf(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])));
-        } else {
-          float m[11];
-#pragma unroll
-          for (int j = 0; j < 10; ++j)
-            m[j] = fmin3(__uint_as_float(r[3 * j]), __uint_as_float(r[3 * j + 1]), __uint_as_float(r[3 * j + 2]));
-          m[10] = fminf(__uint_as_float(r[30]), __uint_as_float(r[31]));
-          const float gm = fmin3(fmin3(m[0], m[1], m[2]), fmin3(m[3], m[4], m[5]),
-                                 fmin3(fmin3(m[6], m[7], m[8]), m[9], m[10]));
-          list_insert<KC>(lst, gm);
-        }
-        const float bound = lst[KC - 1] + eps2;
-#pragma unroll
-        for (int j8 = 0; j8 < 32; j8 += 8) {
-#pragma unroll
-          for (int j = j8; j < j8 + 8; ++j) {
-            const uint32_t tagged = (r[j] & 0xFFFFF800u) + (uint32_t)(pos0 + j);
-            // predicated append (no branch): room for 8 more entries is guaranteed by the compaction below
-            asm volatile(
-                "{\n\t"
-                ".reg .pred p;\n\t"
-                "setp.le.f32 p, %1, %2;\n\t"
-                "@p st.shared.b32 [%0], %3;\n\t"
-                "@p add.u32 %0, %0, 512;\n\t"
-                "}\n"
-                : "+r"(waddr)
-                : "f"(__uint_as_float(r[j])), "f"(bound), "r"(tagged)
-                : "memory");
-          }
-          if (__any_sync(0xffffffffu, waddr > list_base + (kListCap - 8) * 512)) {
-            // whole warp: drop what today's tighter bound already excludes
-            waddr = list_base + 512 * list_compact(my_list, (int)((waddr - list_base) >> 9), bound);
-            if (waddr > list_base + (kListCap - 8) * 512) {   // more than that inside the band: brute force later
-              overflow = true;
-              waddr = list_base;
-            }
-          }
-        }
-      };
-
-      for (int c = 0; c < nchunks; ++c, ++bcount) {
-        const uint32_t acc = bcount % kAccStages, aph = (bcount / kAccStages) & 1;
-        if (experiment == 80) continue;
-        ptx::mbar_wait_backoff(&ss->t_full[acc], aph, 100);
-        ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (acc * kTilesPerItem + mt) * kChunkN;
-        const int cpos = c * kChunkN;
-        if (experiment >= 77) {   // timing experiment: TMA + MMA pipeline only
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&ss->t_empty[acc]);
-          continue;
-        }
-        uint32_t r0[32], r1[32];
-        ptx::tmem_ld_32x32(taddr, r0);
-        ptx::tmem_ld_wait();
-#pragma unroll 1
-        for (int h = 0; h < kChunkN / 64; ++h) {
-          ptx::tmem_ld_32x32(taddr + 64 * h + 32, r1);      // in flight while r0 is processed
-          process(r0, cpos + 64 * h, c == 0 && h == 0);
-          ptx::tmem_ld_wait();
-          if (h + 1 < kChunkN / 64) {
-            ptx::tmem_ld_32x32(taddr + 64 * h + 64, r0);
-          } else {
-            ptx::tc_fence_before();                          // all TMEM reads of this stage are done
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&ss->t_empty[acc]);
-          }
-          process(r1, cpos + 64 * h + 32, false);
-          ptx::tmem_ld_wait();
-        }
-      }
-      const int cnt = (int)((waddr - list_base) >> 9);
-      // end of the cell: filter with the final bound, emit candidate target indices
-      int ns_stat = 0;
-      if (valid) {
-        const int ci = cell % g.ncellx, cj = cell / g.ncellx;
-        int cimin, cimax, cjmin, cjmax;
-        cell_range(px, g.cellw, g.ncellx, g.R, &cimin, &cimax);
-        cell_range(py, g.cellh, g.ncelly, g.R, &cjmin, &cjmax);
-        const int blk = (ci - cimin) * (cjmax - cjmin + 1) + (cj - cjmin);
-        const size_t task = (size_t)pix * g.nblk + blk;
-        const float bound = lst[KC - 1] + eps2;
-        int ns = 0;
-        for (int e = 0; e < cnt; ++e) {
-          const uint32_t en = my_list[e * kTileM];
-          if (__uint_as_float(en & 0xFFFFF800u) <= bound) {
-            if (ns < kCand) cand[task * kCand + ns] = (uint16_t)(((en & 0x7FFu) * (uint32_t)g.stride_s) % (uint32_t)g.T);
-            ++ns;
-          }
-        }
-        cand_cnt[task] = (overflow || ns > kCand) ? 255 : (uint8_t)ns;
-        if (overflow) atomicAdd(counters + 1, 1);          // diagnostics (rare)
-        else if (ns > kCand) atomicAdd(counters + 2, 1);
-        else ns_stat = ns;
-      }
-      if (counters_on) {   // diagnostics: one atomic per warp and cell
-        const int tot = __reduce_add_sync(0xffffffffu, ns_stat);
-        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 4), (unsigned long long)tot);
-      }
     }
-      }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -637,7 +469,7 @@ __device__ __forceinline__ double exact_dist(const float* __restrict__ q, const 
 // candidate array entry -> target index inside the cell: the two-pass selection stores the POSITION in the cell's
 // permuted target order (the modulo is cheaper here, one lane per candidate, than in the selection's hit loop)
 __device__ __forceinline__ int cand_index(const KnnTcGeom& g, uint32_t c) {
-  return kTwoPass ? (int)((c * (uint32_t)g.stride_s) % (uint32_t)g.T) : (int)c;
+  return (int)((c * (uint32_t)g.stride_s) % (uint32_t)g.T);
 }
 
 template <int KC>
@@ -1011,12 +843,12 @@ static int run_tc(const float* desc_src, const float* desc_tgt, const flowb200_p
   CUtensorMap mq;
   if (!make_map(&mq, q16, (uint64_t)g.W, (uint64_t)g.H, kTileW, kTileH)) return FLOWB200_ECUDA;
   const int n_items = ncell * g.tiles_x * g.tiles_y;
-  const size_t smem = (size_t)kTileBytes * (kTilesPerItem + kBStages) + (size_t)kListBytes +
+  const size_t smem = (size_t)kTileBytes * (kTilesPerItem + kBStages) +
                       sizeof(SelSmem) + 1024;
   auto kern = dbg_scores ? knn_select_kernel<KC, true> : knn_select_kernel<KC, false>;
   FB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(L.grid, n_items);
-  kern<<<grid, kSelThreads, smem, stream>>>(mq, t16, g, n_items, qinfo, cellinfo, cand, cnt, fb_count, stats != nullptr, getenv("FLOWB200_KNN_EXPERIMENT") ? atoi(getenv("FLOWB200_KNN_EXPERIMENT")) : 0, dbg_scores);
+  kern<<<grid, kSelThreads, smem, stream>>>(mq, t16, g, n_items, qinfo, cellinfo, cand, cnt, fb_count, stats != nullptr, dbg_scores);
   FB_LAUNCH_CHECK();
 
   const unsigned rgrid = (unsigned)((n * 16 + 255) / 256);
