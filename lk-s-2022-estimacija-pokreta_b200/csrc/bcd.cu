@@ -600,11 +600,11 @@ static size_t legacy_workspace_bytes(int H, int W, int K) {
   return align_up((col > row ? col : row) * Kpad * sizeof(uint16_t)) + align_up((size_t)H * W * K * sizeof(uint32_t));
 }
 
-// The int32 programme runs on compiled K-sets (bcd_ksets.cu) unless FLOWB200_BCD_LEGACY is set in the environment
-// (or tpsi > 8); the float64 modes always run the implementation in this file.
+// Every mode runs on compiled K-sets (bcd_ksets.cu) unless FLOWB200_BCD_LEGACY is set in the environment (read at every
+// call: the tests use it to compare the two implementations) or tpsi > 8; the implementation in this file re-evaluates
+// the K-sets at every chain step.
 static bool use_ksets(int tpsi, int cost_shift) {
-  static const bool legacy = getenv("FLOWB200_BCD_LEGACY") != nullptr;
-  return !legacy && tpsi >= 1 && tpsi <= 8 && cost_shift >= 4;
+  return getenv("FLOWB200_BCD_LEGACY") == nullptr && tpsi >= 1 && tpsi <= 8 && cost_shift >= 4;
 }
 
 extern "C" size_t flowb200_bcd_workspace_bytes(int H, int W, int K) {
@@ -635,6 +635,15 @@ extern "C" int flowb200_bcd(const int32_t* pvec, const void* cost, const int32_t
                                           cost_shift, sweeps, labels_per_sweep, workspace, workspace_bytes, stream);
     return launch_sweeps_ksets<float>(pvec, static_cast<const float*>(cost), nprop, labels, H, W, K, lamda, tpsi,
                                       cost_shift, sweeps, labels_per_sweep, workspace, workspace_bytes, stream);
+  }
+  if (!int_mode && use_ksets(tpsi, 4)) {   // the float64 programme on the same records (shift -1)
+    if (bcd_mode == FLOWB200_BCD_FP64_F32COST)
+      return launch_sweeps_ksets<float>(pvec, static_cast<const float*>(cost), nprop, labels, H, W, K, lamda, tpsi, -1,
+                                        sweeps, labels_per_sweep, workspace, workspace_bytes, stream);
+    if (bcd_mode == FLOWB200_BCD_FP64_F64COST)
+      return launch_sweeps_ksets<double>(pvec, static_cast<const double*>(cost), nprop, labels, H, W, K, lamda, tpsi, -1,
+                                         sweeps, labels_per_sweep, workspace, workspace_bytes, stream);
+    return FLOWB200_EINVAL;
   }
   if (workspace_bytes < legacy_workspace_bytes(H, W, K)) return FLOWB200_EWORKSPACE;
   uint16_t* bp = static_cast<uint16_t*>(workspace);

@@ -42,7 +42,8 @@ __device__ __forceinline__ int bucket_key(int32_t v, int bshift) {
   return (bkt_y(vec_dy(v) >> bshift) << 6) | bkt_x(vec_dx(v) >> bshift);
 }
 
-// K-set implementation entry (bcd_ksets.cu).  CostT = int32_t (units of 2^-shift) or float (quantised on the fly).
+// K-set implementation entry (bcd_ksets.cu).  CostT = int32_t (units of 2^-shift) or float (quantised on the fly);
+// shift < 0: the float64 programme (python bcd.py's own arithmetic) on float / double data costs.
 template <typename CostT>
 int launch_sweeps_ksets(const int32_t* pvec, const CostT* cost, const int32_t* nprop, int32_t* labels, int H, int W,
                         int K, double lamda, int tpsi, int shift, int sweeps, int32_t* labels_per_sweep,

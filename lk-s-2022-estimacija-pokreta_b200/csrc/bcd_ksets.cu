@@ -9,27 +9,22 @@
 //                      Records are carved from an arena with one atomic cursor; a 64-bit descriptor per record
 //                      (offset | size) is the only index.  All (pixel, orientation) pairs are independent, so this
 //                      kernel is throughput bound, unlike the chains.
-//   kset_chain32_kernel  one CTA per chain, one thread per label position.  Thread 0 streams the chain's records into
-//                      a ring of shared-memory slots with bulk asynchronous copies (TMA engine, mbarrier completion)
-//                      four steps ahead; a step is: wait for the slot, min over the label's entry list of
-//                      key[k] + (L1 << S), add the unary term, publish the new key, one block barrier.
-//   kset_chain_kernel  the same with 64-bit keys: runs only the chains the 32-bit kernel could not certify.
-//
-// Keys.  "Smallest dp, lowest label on ties" (np.argmin, python bcd.py:155/:175/:234) is one unsigned minimum of
-// (dp << 9 | label).  In 32 bits that leaves 23 bits for dp, so the 32-bit kernel keeps dp RELATIVE to the block
-// minimum of two steps earlier (minima never decrease along a chain) and SATURATES: a key >= satkey (2^31) means "too
-// large to represent", and every candidate derived from it is >= satkey again.  Because of quirk Q1 (the truncation
-// candidate is ignored when S_l is not empty, :170-176) the spread of dp over the labels of a pixel is unbounded, so
-// saturated labels do occur -- but a key below satkey is exact (it is the minimum over candidates of which every one
-// below satkey is exact), its back-pointer is exact, and its predecessor is below satkey too.  Hence the whole
-// backtracked path is exact whenever the final minimum is below satkey; otherwise the chain is flagged and re-run by the
-// 64-bit kernel (dp << 32 | label, no saturation), launched right behind.  FLOWB200_KSET_SATBITS lowers satkey for
-// tests that want to see the fallback at work.
+//   kset_chain32_kernel  one CTA per chain, one thread per label position.  One thread streams the chain's records
+//                      into a ring of shared-memory slots with bulk asynchronous copies (TMA engine, mbarrier
+//                      completion) four steps ahead; a step is: wait for the slot, lexicographic minimum over the
+//                      label's entry list of (dp[k] + (L1 << S), k), add the unary term, publish the new dp, one block
+//                      barrier.  dp is a uint32 in units of 2^-S; (dp, label) pairs order like np.argmin does
+//                      (python bcd.py:155/:175/:234: smallest value, lowest index on ties).
+//   kset_chain_kernel  the generic variant (64-bit keys dp << 32 | label, steps without a stored record evaluated
+//                      densely): runs only the chains that have such a step (flagged by the first kernel).
+//   kset_chainf64_kernel  the float64 programme (FLOWB200_BCD_FP64_*) on the same records.
 //
 // A record that does not fit (arena exhausted, staging or slot too small, list longer than 124, data cost out of 16
 // bits) gets descriptor 0 and
 // its step is evaluated densely from pvec/cost inside the chain kernel, so any workspace size gives the exact result.
 // Precondition of the int32 modes: 0 <= m < 65536 for every used slot (the uint32 dp bound of make_plan assumes it).
+#include <math_constants.h>
+
 #include <algorithm>
 #include <type_traits>
 
@@ -429,7 +424,7 @@ struct ChainArgs {
   int32_t* flags;     // per chain of the launch: the 32-bit kernel sets 1 when it cannot certify its result
   int H, W, K, Kpad, phase, chain0, tpsi, shift, slot_shift;   // chain = chain0 + blockIdx.x; 1 << slot_shift slots
   uint32_t slot_bytes;
-  uint32_t satkey;    // 32-bit keys >= satkey are "too large to represent"
+  int force_generic;  // (tests) leave every chain to the generic kernel
   double lamda;
 };
 
@@ -493,7 +488,7 @@ __device__ __forceinline__ void chain64_body(const ChainArgs& a) {
   __shared__ Key wred[2][kMaxWarps];           // warp minima of a step (infinite for warps without labels)
   __shared__ uint32_t present_s[4];
   __shared__ __align__(8) uint64_t mbar[4];
-  if (a.flags[blockIdx.x] == 0) return;   // (uniform) certified by the 32-bit kernel
+  if (a.flags[blockIdx.x] == 0) return;   // (uniform) done by the 32-bit kernel
 
   const ChainGeom g = chain_geom(a.phase, a.chain0 + (int)blockIdx.x, a.H, a.W);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -648,25 +643,234 @@ __device__ __forceinline__ void chain64_body(const ChainArgs& a) {
   backtrack<T>(a, g, (int)key_label(block_min(g.len - 1)), path, slots, S);
 }
 
+// The float64 programme on the same records (FLOWB200_BCD_FP64_*: arbitrary data costs, the reference's own arithmetic
+// and operation order, python bcd.py:118-120, :152-176): dp is a double per label, candidates are compared as
+// (value, label) pairs -- np.argmin takes the lowest label among equal values --, and the data cost comes from the
+// cost array (the record's 16-bit cost field is unused).  One thread per label position, every chain of the launch.
+__device__ __forceinline__ void warp_argmin_f64(double& val, int& idx) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, val, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+    if (ov < val || (ov == val && oi < idx)) {
+      val = ov;
+      idx = oi;
+    }
+  }
+}
+
+template <typename CostT, int T>
+__device__ __forceinline__ void chainf64_body(const ChainArgs& a) {
+  constexpr int NW = T / 32;
+  constexpr int kNone = 0x7fffffff;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(16) double rep_s[2 * 512];   // [2 * k + b]: dp of label k at a step of parity b
+  __shared__ double red_val[2][kMaxWarps];          // per warp: min of (tpsi + dp, label) of a step, lowest label on ties
+  __shared__ int red_idx[2][kMaxWarps];             // (the sum is what the reference minimises, :152-157: it can tie where dp does not)
+  __shared__ uint32_t present_s[4];
+  __shared__ __align__(8) uint64_t mbar[4];
+
+  const ChainGeom g = chain_geom(a.phase, a.chain0 + (int)blockIdx.x, a.H, a.W);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int K = a.K, Kpad = a.Kpad, tpsi = a.tpsi;
+  const int S = 1 << a.slot_shift, smask = S - 1;
+  const unsigned long long* dsc = a.desc + (size_t)(a.phase & 1) * a.H * a.W;
+  const CostT* cost = static_cast<const CostT*>(a.cost);
+  const double lamda = a.lamda;
+
+  int32_t* oldvec = reinterpret_cast<int32_t*>(smem_raw);
+  int32_t* vprev = oldvec + g.len;
+  uint16_t* path = reinterpret_cast<uint16_t*>(vprev + Kpad);
+  unsigned char* slots = smem_raw + chain_fixed_smem(Kpad, g.len);
+  auto pixel = [&](int i) { return (g.sy + i * g.ystep) * a.W + (g.sx + i * g.xstep); };
+
+  for (int i = t; i < g.len; i += T) {
+    const int p = pixel(i);
+    oldvec[i] = a.pvec[(size_t)p * K + a.labels[p]];
+  }
+  if (t == 0) {
+    for (int s = 0; s < S; ++s) ptx::mbar_init(&mbar[s], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+
+  unsigned long long d_next = 0;
+  auto issue = [&](int i, unsigned long long d) {
+    const int slot = i & smask;
+    const uint32_t bytes = (uint32_t)(d >> 40) << 4;
+    present_s[slot] = bytes;
+    if (bytes) {
+      ptx::mbar_arrive_expect_tx(&mbar[slot], bytes);
+      ptx::bulk_load(slots + (size_t)slot * a.slot_bytes, a.arena + ((d & ((1ull << 40) - 1)) << 4), bytes, &mbar[slot]);
+    } else {
+      ptx::mbar_arrive(&mbar[slot]);
+    }
+  };
+  if (t == 0) {
+    for (int i = 0; i < S && i < g.len; ++i) issue(i, dsc[pixel(i)]);
+    if (S < g.len) d_next = dsc[pixel(S)];
+  }
+
+  // block argmin of what the warps left in red_val / red_idx[step & 1]
+  auto block_argmin = [&](int step, double& v, int& k) {
+    v = red_val[step & 1][0];
+    k = red_idx[step & 1][0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) {
+      const double ov = red_val[step & 1][w];
+      const int oi = red_idx[step & 1][w];
+      if (ov < v || (ov == v && oi < k)) {
+        v = ov;
+        k = oi;
+      }
+    }
+  };
+  const int sgn = g.ystep + g.xstep;   // +1: the image coordinate grows with the step index
+  uint16_t* bp_row = a.bp + (size_t)blockIdx.x * g.len * Kpad;
+  double last_dp = CUDART_INF;
+  int last_label = kNone;
+
+  for (int i = 0; i < g.len; ++i, bp_row += Kpad) {
+    const int slot = i & smask;
+    ptx::mbar_wait(&mbar[slot], (uint32_t)(i >> a.slot_shift) & 1u);
+    const uint32_t present = present_s[slot];
+    const int prv = (i & 1) ^ 1;
+    double dpv = CUDART_INF;
+    int mine = kNone;
+    // side terms (sidepsi :84-88): the neighbour on the +1 side of the chain axis first, as the reference adds them
+    const int ip = i + sgn, im = i - sgn;
+    const bool has_p = ip >= 0 && ip < g.len, has_m = im >= 0 && im < g.len;
+    const int32_t ov_p = has_p ? oldvec[ip] : 0, ov_m = has_m ? oldvec[im] : 0;
+    // dp of label `orig` (vector dy, dx) from the minimum (best, arg) over the previous step's candidates
+    auto finish = [&](int dy, int dx, int orig, double best, int arg, const int p) {
+      const int psi_p = has_p ? min(tpsi, l1_vec(dy, dx, ov_p)) : 0;
+      const int psi_m = has_m ? min(tpsi, l1_vec(dy, dx, ov_m)) : 0;
+      const double lc = __dmul_rn(lamda, (double)cost[(size_t)p * K + orig]);
+      if (i == 0) {   // (psi+ + psi-) + lamda*lcost   (:118-120)
+        dpv = __dadd_rn((double)(psi_p + psi_m), lc);
+      } else {        // (lamda*lcost + psi+) + psi-, then m + that   (:161-162, :176)
+        if (arg == kNone) block_argmin(i - 1, best, arg);   // quirk Q1: min_k (tpsi + dp_prev[k]), lowest k (:152-157),
+                                                           // only for an empty K-set
+        dpv = __dadd_rn(best, __dadd_rn(__dadd_rn(lc, (double)psi_p), (double)psi_m));
+        bp_row[orig] = (uint16_t)arg;
+      }
+      mine = orig;
+      rep_s[2 * orig + (i & 1)] = dpv;
+    };
+    if (present) {
+      const unsigned char* rec = slots + (size_t)slot * a.slot_bytes;
+      const uint4 hdr = *reinterpret_cast<const uint4*>(rec);
+      if (t < (int)hdr.x) {
+        const uint2 st = *reinterpret_cast<const uint2*>(rec + hdr.z + 8 * t);
+        double best = CUDART_INF;
+        int arg = kNone;
+        if (i > 0) {
+          const int ng = (int)(st.y >> 25);
+          const uint32_t g0 = *reinterpret_cast<const uint16_t*>(rec + kRecHeader + 2 * t);
+          const uint2* eg = reinterpret_cast<const uint2*>(rec + hdr.w) + g0;
+          for (int gi = 0; gi < ng; ++gi) {
+            const uint2 w = eg[gi];
+            const uint32_t e[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (!(e[j] & 0x1000u)) {   // (not a padding entry)
+                const int k = (int)((e[j] >> 3) & 511u);
+                const double cand = __dadd_rn(rep_s[2 * k + prv], (double)(e[j] >> 13));
+                if (cand < best || (cand == best && k < arg)) {   // np.argmin: lowest k wins ties
+                  best = cand;
+                  arg = k;
+                }
+              }
+          }
+        }
+        finish(vec_dy((int32_t)st.x), vec_dx((int32_t)st.x), (int)((st.y >> 16) & 511u), best, arg, pixel(i));
+      }
+    } else {
+      // dense step: the record was not stored; evaluate the K-set from the proposal arrays
+      const int p = pixel(i);
+      const int n = a.nprop[p];
+      int nq = 0;
+      if (i > 0) {
+        const int q = pixel(i - 1);
+        nq = a.nprop[q];
+        for (int k = t; k < nq; k += T) vprev[k] = a.pvec[(size_t)q * K + k];
+      }
+      __syncthreads();
+      if (t < n) {
+        const int32_t v = a.pvec[(size_t)p * K + t];
+        const int dy = vec_dy(v), dx = vec_dx(v);
+        double best = CUDART_INF;
+        int arg = kNone;
+        for (int k = 0; k < nq; ++k) {
+          const int l1 = l1_vec(dy, dx, vprev[k]);
+          if (l1 < tpsi) {
+            const double cand = __dadd_rn(rep_s[2 * k + prv], (double)l1);
+            if (cand < best) {   // (k ascending: the first minimum is the lowest k)
+              best = cand;
+              arg = k;
+            }
+          }
+        }
+        finish(dy, dx, t, best, arg, p);
+      }
+    }
+    last_dp = dpv;
+    last_label = mine;
+    {
+      double wv = __dadd_rn((double)tpsi, dpv);
+      int wi = mine;
+      warp_argmin_f64(wv, wi);
+      if (lane == 0) {
+        red_val[i & 1][warp] = wv;
+        red_idx[i & 1][warp] = wi;
+      }
+    }
+    __syncthreads();
+    if (t == 0 && i + S < g.len) {
+      issue(i + S, d_next);
+      if (i + S + 1 < g.len) d_next = dsc[pixel(i + S + 1)];
+    }
+  }
+
+  // final label: lowest-index argmin of dp_last (:231-237)
+  warp_argmin_f64(last_dp, last_label);
+  const int fin = g.len & 1;   // the buffer the last step's reduction did not use
+  if (lane == 0) {
+    red_val[fin][warp] = last_dp;
+    red_idx[fin][warp] = last_label;
+  }
+  __syncthreads();
+  double bv;
+  int lab;
+  block_argmin(fin, bv, lab);
+  backtrack<T>(a, g, lab, path, slots, S);
+}
+
 // ------------------------------------------------------------------------------------------------
 // The 32-bit chain kernel proper: one thread per label position, as few instructions per step as possible.  Measured
 // (ncu, profiles/): a chain step is bound by the NUMBER of warp instructions it issues -- an SM holds ~3 chains whose
-// warps each run one dependent instruction stream at ~7 cycles per instruction -- so what counts is: warps without
-// labels go straight to the barrier; the key array is 4 KB aligned, so that the shared-memory address of an entry's key
-// is ONE logic operation on the packed entry word (mask | base | buffer); the cost shift is a template parameter (12 is
-// what the scripts and the benchmark use; 0 = run time); the last warp, which has no labels or the shortest lists,
-// streams the records and reduces the block minimum for the rebase.  Chains with a record that was not stored are left
-// to the generic 64-bit kernel (flags[chain] = 1), which evaluates such steps densely.
+// warps each run one dependent instruction stream at ~7 cycles per instruction -- so what counts is: dp is a plain
+// uint32 in units of 2^-shift (make_plan bounds a whole chain below 2^32: no rebasing); "smallest dp, lowest label
+// on ties" (np.argmin, python bcd.py:155/:175/:234) is the lexicographic minimum of (dp, label field of the entry) --
+// two compares on 32-bit registers; warps without labels go straight to the barrier; the dp array is 4 KB aligned, so
+// that the shared-memory address of an entry's dp is one logic operation on the packed entry word (mask | base |
+// buffer); the cost shift is a template parameter (12 is what the scripts and the benchmark use; 0 = run time); the
+// last warp, which has no labels or the shortest lists, streams the records.  Chains with a record that was not stored
+// are left to the generic kernel (flags[chain] = 1), which evaluates such steps densely.
+// (Keys of (dp relative to the running minimum) << 9 | label, one unsigned minimum per entry, were built first and are
+// NOT exact: because of quirk Q1 -- no truncation candidate for a non-empty K-set, :170-176 -- whole families of labels
+// fall behind the minimum by ~16 units per step, overflow any 22-bit field within ~64 steps, and now and then catch up
+// again: one column chain in 512 went wrong at 1024x436.)
 // ------------------------------------------------------------------------------------------------
-constexpr int kKeyBytes = 4096;   // keys of labels 0..510 in two buffers; the slot of label 511 stays infinite (null entries)
+constexpr int kKeyBytes = 4096;   // dp of labels 0..510 in two buffers; the slot of label 511 stays infinite (null entries)
 
 template <typename CostT, int T, int SHIFT>
 __device__ __forceinline__ void chain32_body(const ChainArgs& a) {
   constexpr int NW = T / 32;
   constexpr uint32_t kInf = 0xFFFFFFFFu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint32_t wred[2][kMaxWarps];   // warp minima of a step's keys (infinite for warps without labels)
-  __shared__ uint32_t delta_s[2];           // rebase of a step, by its parity
+  __shared__ uint32_t wred_v[2][kMaxWarps];   // per warp: minimum dp of a step (infinite for warps without labels) ...
+  __shared__ uint32_t wred_l[2][kMaxWarps];   // ... and the lowest label that has it
   __shared__ __align__(8) uint64_t mbar[4];
   __shared__ int absent_s;
 
@@ -678,7 +882,7 @@ __device__ __forceinline__ void chain32_body(const ChainArgs& a) {
   const unsigned long long* dsc = a.desc + (size_t)(a.phase & 1) * a.H * a.W;
   const int len = g.len;
 
-  // dynamic shared memory: [pad] keys (4 KB aligned) | oldvec | path | record slots
+  // dynamic shared memory: [pad] dp (4 KB aligned) | oldvec | path | record slots
   const uint32_t dyn0 = ptx::smem_u32(smem_raw);
   const uint32_t pad = (0u - dyn0) & (uint32_t)(kKeyBytes - 1);
   uint32_t* rep_s = reinterpret_cast<uint32_t*>(smem_raw + pad);   // [2 * k + parity]
@@ -697,7 +901,7 @@ __device__ __forceinline__ void chain32_body(const ChainArgs& a) {
       oldvec[i] = a.pvec[(size_t)p * K + a.labels[p]];
       absent |= (dsc[p] >> 40) == 0;
     }
-    if (absent || K > 511) absent_s = 1;   // (label 511's key slot is the padding entries' infinity)
+    if (absent || K > 511 || a.force_generic) absent_s = 1;   // (label 511's slot is the padding entries' infinity)
   }
   if (t < 2) rep_s[2 * 511 + t] = kInf;
   if (t == 0) {
@@ -709,6 +913,7 @@ __device__ __forceinline__ void chain32_body(const ChainArgs& a) {
     if (t == 0) a.flags[blockIdx.x] = 1;
     return;
   }
+  if (t == 0) a.flags[blockIdx.x] = 0;
 
   const bool producer = t == T - 32;
   unsigned long long d_next = 0;
@@ -723,12 +928,16 @@ __device__ __forceinline__ void chain32_body(const ChainArgs& a) {
     if (S < len) d_next = dsc[pixel(S)];
   }
 
-  const uint32_t tpsi_key = (uint32_t)tpsi << (shift + 9);
-  const uint32_t l1_mul = 1u << (shift - 4), l1_shr = (uint32_t)(20 - shift);   // (4 <= shift <= 14)
-  const uint32_t satkey = a.satkey;
+  const uint32_t tpsi_dp = (uint32_t)tpsi << shift;
   uint16_t* bp_row = a.bp + (size_t)blockIdx.x * len * Kpad;   // row of step i (advanced every step)
   const uint32_t mbar_u32 = ptx::smem_u32(mbar);
-  uint32_t delta_mine = 0;   // last warp: the rebase of the current step
+  // (value, label field) pairs: lexicographic minimum with two compares on the 32-bit halves
+  auto lex_min = [](uint32_t& bv, uint32_t& bk, uint32_t v, uint32_t k) {
+    const unsigned long long x = ((unsigned long long)v << 32) | k, y = ((unsigned long long)bv << 32) | bk;
+    const bool lt = x < y;
+    bv = lt ? v : bv;
+    bk = lt ? k : bk;
+  };
 
   for (int i = 0; i < len; ++i, bp_row += Kpad) {
     const int slot = i & smask;
@@ -736,7 +945,7 @@ __device__ __forceinline__ void chain32_body(const ChainArgs& a) {
     const unsigned char* rec = slots + (size_t)slot * a.slot_bytes;
     const uint4 hdr = *reinterpret_cast<const uint4*>(rec);   // n, entry groups, struct offset, entry offset
     const int n = (int)hdr.x;
-    uint32_t key = kInf;
+    uint32_t dp = kInf, mine = kInf;
     if (t < n) {
       const uint2 st = *reinterpret_cast<const uint2*>(rec + hdr.z + 8 * t);
       const uint32_t orig = (st.y >> 16) & 511u;
@@ -746,53 +955,50 @@ __device__ __forceinline__ void chain32_body(const ChainArgs& a) {
       uint32_t psi = 0;
       if (i + 1 < len) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, oldvec[i + 1]));
       if (i > 0) psi += (uint32_t)min(tpsi, l1_vec(dy, dx, oldvec[i - 1]));
-      const uint32_t U = (st.y & 0xFFFFu) + (psi << shift);
+      dp = (st.y & 0xFFFFu) + (psi << shift);   // dp_0 = unary (:118-120)
       if (i > 0) {
         const uint32_t ng = st.y >> 25;
         const uint32_t g0 = *reinterpret_cast<const uint16_t*>(rec + kRecHeader + 2 * t);
         const uint2* eg = reinterpret_cast<const uint2*>(rec + hdr.w) + g0;
         const uint32_t base = rep_u32 | ((uint32_t)((i & 1) ^ 1) << 2);   // previous step's buffer
-        uint32_t acc0 = kInf, acc1 = kInf;
+        uint32_t v0 = kInf, k0 = kInf, v1 = kInf, k1 = kInf;   // two independent running minima
         for (uint32_t gi = 0; gi < ng; ++gi) {
           const uint2 w = eg[gi];
-          uint32_t c0 = ptx::lds_u32((w.x & 0xFF8u) | base);
-          uint32_t c1 = ptx::lds_u32(((w.x >> 16) & 0xFF8u) | base);
-          uint32_t c2 = ptx::lds_u32((w.y & 0xFF8u) | base);
-          uint32_t c3 = ptx::lds_u32(((w.y >> 16) & 0xFF8u) | base);
-          c0 += (w.x & 0xE000u) * l1_mul;   // L1 << (shift + 9) straight from the packed words
-          c1 += (w.x & 0xE0000000u) >> l1_shr;
-          c2 += (w.y & 0xE000u) * l1_mul;
-          c3 += (w.y & 0xE0000000u) >> l1_shr;
-          acc0 = min(acc0, min(c0, c1));
-          acc1 = min(acc1, min(c2, c3));
+          // an entry: bits 3..11 = previous-pixel label << 3 (= offset of its dp pair), bits 13..15 = L1
+          const uint32_t ka = w.x & 0xFF8u, kb = (w.x >> 16) & 0xFF8u, kc = w.y & 0xFF8u, kd = (w.y >> 16) & 0xFF8u;
+          const uint32_t ca = ptx::lds_u32(ka | base) + (((w.x >> 13) & 7u) << shift);
+          const uint32_t cb = ptx::lds_u32(kb | base) + ((w.x >> 29) << shift);
+          const uint32_t cc = ptx::lds_u32(kc | base) + (((w.y >> 13) & 7u) << shift);
+          const uint32_t cd = ptx::lds_u32(kd | base) + ((w.y >> 29) << shift);
+          lex_min(v0, k0, ca, ka);
+          lex_min(v1, k1, cb, kb);
+          lex_min(v0, k0, cc, kc);
+          lex_min(v1, k1, cd, kd);
         }
-        uint32_t acc = min(acc0, acc1);
-        if (ng == 0) {   // quirk Q1: the truncation candidate only for an empty K-set (last warps: lists are sorted)
-          uint32_t m = kInf;
+        lex_min(v0, k0, v1, k1);
+        uint32_t arg = k0 >> 3;
+        if (ng == 0) {   // quirk Q1: the truncation candidate min_k (tpsi + dp_prev[k]), lowest k (:152-157), only for an
+                         // empty K-set (last warps: labels are stored by decreasing list length)
+          v0 = kInf;
+          arg = kInf;
 #pragma unroll
-          for (int k = 0; k < NW; ++k) m = min(m, wred[(i - 1) & 1][k]);
-          acc = m + tpsi_key;
+          for (int k = 0; k < NW; ++k) lex_min(v0, arg, wred_v[(i - 1) & 1][k], wred_l[(i - 1) & 1][k]);
+          v0 += tpsi_dp;
         }
-        // rebase, saturate (no wrap: acc < satkey <= 2^31, U < 2^18 + 2^(4 + shift))
-        const uint32_t delta = delta_s[i & 1];
-        const uint32_t v = (acc & ~511u) - delta + (U << 9);
-        key = (acc >= satkey ? satkey : min(v, satkey)) | orig;
-        bp_row[orig] = (uint16_t)(acc & 511u);
-      } else {   // dp_0 = unary (:118-120)
-        key = (U << 9) | orig;
+        dp += v0;
+        bp_row[orig] = (uint16_t)arg;
       }
-      rep_s[2 * orig + (i & 1)] = key;
+      mine = orig;
+      rep_s[2 * orig + (i & 1)] = dp;
     }
-    if (wfirst < n) key = __reduce_min_sync(0xffffffffu, key);   // (warp uniform) else: infinite
-    if (lane == 0) wred[i & 1][warp] = key;
-    if (warp == NW - 1) {   // rebase of step i+1: the block minimum of step i-1 in step i's frame (see the header)
-      uint32_t dn = 0;
-      if (i >= 1) {
-        const uint32_t m = __reduce_min_sync(0xffffffffu, lane < NW ? wred[(i - 1) & 1][lane] : kInf);
-        dn = (m & ~511u) - delta_mine;
-      }
-      if (lane == 0) delta_s[(i + 1) & 1] = dn;
-      delta_mine = dn;
+    if (wfirst < n) {   // (warp uniform) minimum dp of the warp's labels and the lowest label that has it
+      const uint32_t m = __reduce_min_sync(0xffffffffu, dp);
+      mine = __reduce_min_sync(0xffffffffu, dp == m ? mine : kInf);
+      dp = m;
+    }
+    if (lane == 0) {
+      wred_v[i & 1][warp] = dp;
+      wred_l[i & 1][warp] = mine;
     }
     __syncthreads();
     if (producer && i + S < len) {
@@ -801,20 +1007,21 @@ __device__ __forceinline__ void chain32_body(const ChainArgs& a) {
     }
   }
 
-  // final label: lowest-index argmin of dp_last (:231-237) = label field of the last block minimum; a saturated
-  // minimum cannot be certified: the 64-bit kernel redoes the chain
-  uint32_t last = kInf;
+  // final label: lowest-index argmin of dp_last (:231-237)
+  uint32_t bv = kInf, lab = kInf;
 #pragma unroll
-  for (int k = 0; k < NW; ++k) last = min(last, wred[(len - 1) & 1][k]);
-  const bool bad = last >= satkey;   // (uniform)
-  if (t == 0) a.flags[blockIdx.x] = bad ? 1 : 0;
-  if (bad) return;
-  backtrack<T>(a, g, (int)(last & 511u), path, slots, S);
+  for (int k = 0; k < NW; ++k) lex_min(bv, lab, wred_v[(len - 1) & 1][k], wred_l[(len - 1) & 1][k]);
+  backtrack<T>(a, g, (int)lab, path, slots, S);
 }
 
 template <typename CostT, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) kset_chain_kernel(const ChainArgs a) {
   chain64_body<CostT, T>(a);
+}
+
+template <typename CostT, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) kset_chainf64_kernel(const ChainArgs a) {
+  chainf64_body<CostT, T>(a);
 }
 
 template <typename CostT, int T, int MINB, int SHIFT>
@@ -874,23 +1081,17 @@ struct KsetPlan {
   KsetLayout L;
   void (*kern32)(const ChainArgs) = nullptr;   // every chain, 32-bit saturating keys
   void (*kern64)(const ChainArgs) = nullptr;   // the chains the first could not certify
+  void (*kernf64)(const ChainArgs) = nullptr;  // the float64 programme (every chain)
   int T = 0, bshift = 0, slot_shift = 2;
-  uint32_t slot_bytes = 0, satkey = 0x80000000u;
+  uint32_t slot_bytes = 0;
   size_t smem32[2] = {0, 0}, smem64 = 0;   // smem32: by chain orientation (column chains are H long, row chains W)
 };
 
-// satkey of the 32-bit chain kernel: 2^31 unless FLOWB200_KSET_SATBITS (10..31) asks for less, which sends more chains
-// to the 64-bit kernel (tests)
-static uint32_t satkey_from_env() {   // read at every call, so that a test can change it inside one process
-  const char* e = getenv("FLOWB200_KSET_SATBITS");
-  const int bits = e ? atoi(e) : 31;
-  return 1u << (bits < 10 ? 10 : bits > 31 ? 31 : bits);
-}
-
+// shift < 0 selects the float64 programme (kset_chainf64_kernel): the records then carry no data costs
 template <typename CostT>
 static int make_plan(int H, int W, int K, int tpsi, int shift, size_t workspace_bytes, KsetPlan<CostT>* P) {
   if (K > 512 || tpsi < 1 || tpsi > 8) return FLOWB200_EUNSUPPORTED;
-  {   // dp is a uint32
+  if (shift >= 0) {   // dp is a uint32
     const unsigned long long per_step = ((unsigned long long)(3 * tpsi) << shift) + 65535ull;
     if ((unsigned long long)(H > W ? H : W) * per_step >= 0xFFFF0000ull) return FLOWB200_EUNSUPPORTED;
   }
@@ -905,6 +1106,7 @@ static int make_plan(int H, int W, int K, int tpsi, int shift, size_t workspace_
     P->kern32 = shift == 12 ? kset_chain32_kernel<CostT, TT, (MB > 4 ? 4 : MB), 12>                          \
                             : kset_chain32_kernel<CostT, TT, (MB > 4 ? 4 : MB), 0>;                          \
     P->kern64 = kset_chain_kernel<CostT, TT, 1>;                                                             \
+    P->kernf64 = kset_chainf64_kernel<CostT, TT, 1>;                                                         \
     P->T = TT;                                                                                               \
     minb = MB;                                                                                               \
   }
@@ -912,7 +1114,6 @@ static int make_plan(int H, int W, int K, int tpsi, int shift, size_t workspace_
   FB_KS_CASE(384, 3) FB_KS_CASE(512, 2)
 #undef FB_KS_CASE
   if (!P->kern32) return FLOWB200_EUNSUPPORTED;
-  P->satkey = satkey_from_env();
   // ring of record slots: as many (<= 4) as keep `minb` chains per SM resident
   const int maxlen = H > W ? H : W;
   const size_t fixed32 = 4096 + chain32_fixed_smem(maxlen);   // (4096: worst case of the run-time alignment pad)
@@ -926,10 +1127,11 @@ static int make_plan(int H, int W, int K, int tpsi, int shift, size_t workspace_
   P->smem32[1] = 4096 + chain32_fixed_smem(W) + ((size_t)P->slot_bytes << P->slot_shift);
   P->smem64 = fixed64 + ((size_t)P->slot_bytes << P->slot_shift);
   if (fixed32 + ((size_t)P->slot_bytes << P->slot_shift) + 1536 > (size_t)227 * 1024 ||
-      P->smem64 + 1024 + 8704 > (size_t)227 * 1024)
+      P->smem64 + 1024 + 9216 > (size_t)227 * 1024)
     return FLOWB200_EUNSUPPORTED;
   FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fixed32 + ((size_t)P->slot_bytes << P->slot_shift))));
   FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem64));
+  FB_CUDA_CHECK(cudaFuncSetAttribute(P->kernf64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem64));
   return FLOWB200_OK;
 }
 
@@ -957,7 +1159,8 @@ int ksets_prepare(const int32_t* pvec, const CostT* cost, const int32_t* nprop, 
   FB_CUDA_CHECK(cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
   const int bctas = std::min(16, (int)(227 * 1024 / (bsmem + 1024)));
   bk<<<min(2 * npix, max(1, bctas) * kNumSMs), kBuildThreads, bsmem, stream>>>(
-      pvec, cost, nprop, sorig, svec, H, W, K, L.Kst, L.Kpad, tpsi, P.bshift, shift, lamda, P.slot_bytes,
+      pvec, cost, nprop, sorig, svec, H, W, K, L.Kst, L.Kpad, tpsi, P.bshift, shift < 0 ? 0 : shift, shift < 0 ? 0.0 : lamda,
+      P.slot_bytes,
       reinterpret_cast<unsigned char*>(ws + L.arena), (unsigned long long)L.arena_bytes, cursor,
       reinterpret_cast<unsigned long long*>(ws + L.desc), part, nparts);
   FB_LAUNCH_CHECK();
@@ -992,7 +1195,12 @@ int ksets_phase(const int32_t* pvec, const CostT* cost, const int32_t* nprop, in
   a.phase = phase;
   a.chain0 = c0;
   a.flags = reinterpret_cast<int32_t*>(ws + L.flags);
-  a.satkey = P.satkey;
+  a.force_generic = getenv("FLOWB200_KSET_FORCE_GENERIC") != nullptr;   // read at every call (tests)
+  if (shift < 0) {   // float64 programme
+    P.kernf64<<<c1 - c0, P.T, P.smem64, stream>>>(a);
+    FB_LAUNCH_CHECK();
+    return FLOWB200_OK;
+  }
   P.kern32<<<c1 - c0, P.T, P.smem32[phase & 1], stream>>>(a);
   FB_LAUNCH_CHECK();
   P.kern64<<<c1 - c0, P.T, P.smem64, stream>>>(a);   // blocks of certified chains return at once
@@ -1032,6 +1240,7 @@ int launch_sweeps_ksets(const int32_t* pvec, const CostT* cost, const int32_t* n
                                int, int, int, void*, size_t, cudaStream_t);
 FB_KS_INSTANTIATE(int32_t)
 FB_KS_INSTANTIATE(float)
+FB_KS_INSTANTIATE(double)
 #undef FB_KS_INSTANTIATE
 
 }  // namespace flowb200

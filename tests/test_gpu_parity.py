@@ -309,15 +309,13 @@ def test_bcd_int32_any_workspace_size(extra):
         assert np.array_equal(snaps[w], z[f"labels{w + 1:02d}"]), w
 
 
-@pytest.mark.parametrize("satbits", [17, 20, 24])
-def test_bcd_int32_saturation_fallback(satbits, monkeypatch):
-    """The 32-bit chain kernel keeps dp relative and saturating; a chain whose final minimum is saturated is re-run by
-    the 64-bit kernel.  FLOWB200_KSET_SATBITS lowers the saturation point so that some (24), most (20) or all (17:
-    below one step's unary term) chains take that route: the labels stay the reference's (bcd_q12 fixture) and the
-    oracle's on random proposal sets with large integer costs."""
+def test_bcd_int32_generic_kernel(monkeypatch):
+    """Chains that have a step without a stored record are left by the 32-bit kernel to the generic one (64-bit keys,
+    dense steps).  FLOWB200_KSET_FORCE_GENERIC sends every chain that way: the labels stay the reference's (bcd_q12
+    fixture) and the oracle's on random proposal sets with large integer costs."""
     from oracle import bcd as obcd
     ops, ioc, lib = pkg("ops"), pkg("io_contract"), pkg("_lib")
-    monkeypatch.setenv("FLOWB200_KSET_SATBITS", str(satbits))
+    monkeypatch.setenv("FLOWB200_KSET_FORCE_GENERIC", "1")
     z = load_npz("bcd_q12")
     sweeps, shift = int(z["meta"][5]), int(z["meta"][6])
     labels = dev(z["labels00"], torch.int32)
@@ -325,17 +323,43 @@ def test_bcd_int32_saturation_fallback(satbits, monkeypatch):
                     labels, sweeps, mode=lib.BCD_INT32, cost_shift=shift, per_sweep=True).cpu().numpy()
     for w in range(sweeps):
         assert np.array_equal(snaps[w], z[f"labels{w + 1:02d}"]), w
-    rng = np.random.default_rng(satbits)
+    rng = np.random.default_rng(5)
     H, W, K = 38, 45, 96
     prop = rng.integers(-14, 15, (H, W, K, 2)).astype(np.int64)
     nprop = rng.integers(K // 2, K + 1, (H, W)).astype(np.int64)
     m = rng.integers(0, 60000, (H, W, K)).astype(np.int64)          # near the 16-bit limit of the data cost
     lab0 = (rng.integers(0, 1 << 30, (H, W)) % nprop).astype(np.int64)
     want = obcd.ceo_bcd(prop, 20.0 * m / 4096.0, nprop, lab0, 2)
-    labels = dev(lab0, torch.int32)
-    snaps = ops.bcd(dev(ioc.pack_proposals(prop)), dev(m, torch.int32), dev(nprop, torch.int32), labels, 2,
-                    mode=lib.BCD_INT32, cost_shift=12, per_sweep=True).cpu().numpy()
-    assert np.array_equal(snaps[0], want[0]) and np.array_equal(snaps[1], want[1])
+    for force in (True, False):
+        if not force:
+            monkeypatch.delenv("FLOWB200_KSET_FORCE_GENERIC")
+        labels = dev(lab0, torch.int32)
+        snaps = ops.bcd(dev(ioc.pack_proposals(prop)), dev(m, torch.int32), dev(nprop, torch.int32), labels, 2,
+                        mode=lib.BCD_INT32, cost_shift=12, per_sweep=True).cpu().numpy()
+        assert np.array_equal(snaps[0], want[0]) and np.array_equal(snaps[1], want[1]), force
+
+
+def test_bcd_fp64_ksets_equal_legacy_and_any_workspace(monkeypatch):
+    """The float64 modes run on the compiled K-sets too (what `bcd.py` uses on reference-written files).  They equal
+    the first implementation (bcd.cu, K-sets re-evaluated at every step; FLOWB200_BCD_LEGACY) after every sweep, with
+    every record stored, none (dense steps) or some, on the reference's unquantised costs."""
+    ops, ioc, lib = pkg("ops"), pkg("io_contract"), pkg("_lib")
+    z = load_case("pair_b")
+    sweeps = 2
+    pvec = dev(ioc.pack_proposals(z["b0_proposals"]))
+    nprop = dev(z["b0_nprop"], torch.int32)
+    lab0 = dev(z["b0_labels00"], torch.int32)
+    H, W, K = pvec.shape
+    L = lib.load()
+    lo, hi = L.flowb200_bcd_min_workspace_bytes(H, W, K), L.flowb200_bcd_workspace_bytes(H, W, K)
+    for mode, cost in ((lib.BCD_FP64_F32COST, dev(z["b0_lcosts"], torch.float32)),
+                       (lib.BCD_FP64_F64COST, dev(z["b0_lcosts"] * 1.0000001, torch.float64))):
+        monkeypatch.setenv("FLOWB200_BCD_LEGACY", "1")
+        want = ops.bcd(pvec, cost, nprop, lab0.clone(), sweeps, mode=mode, per_sweep=True)
+        monkeypatch.delenv("FLOWB200_BCD_LEGACY")
+        for nb in (None, lo, lo + (hi - lo) // 7):
+            got = ops.bcd(pvec, cost, nprop, lab0.clone(), sweeps, mode=mode, per_sweep=True, workspace_bytes=nb)
+            assert torch.equal(got, want), (mode, nb)
 
 
 def test_bcd_int32_on_float_costs_equals_quantise_then_int32():

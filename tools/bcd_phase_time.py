@@ -49,8 +49,19 @@ ops.bcd(pv, lc, npr, whole, sweeps, **kw)
 assert torch.equal(whole, l2), "flowb200_bcd differs from prepare + phases"
 m = ops.quantise_costs(lc, p.lamda, p.cost_shift)
 lq = torch.where(lc == 1000.0, torch.full_like(lc, 1000.0, dtype=torch.float64), m.double() * (20.0 / (1 << p.cost_shift)))
+os.environ["FLOWB200_BCD_LEGACY"] = "1"      # bcd.cu: K-sets re-evaluated at every step (independent implementation)
 ref = lab.clone()
 ops.bcd(pv, lq, npr, ref, sweeps, mode=lib.BCD_FP64_F64COST)
+del os.environ["FLOWB200_BCD_LEGACY"]
 ok = torch.equal(ref, l2)
-print("labels equal to the float64 implementation:", ok, "| moved", float((l2 != lab).float().mean()))
+print("labels equal to the float64 implementation (bcd.cu):", ok, "| moved", float((l2 != lab).float().mean()))
 assert ok
+# the float64 programme on the K-set records (what bcd.py runs on reference-written files)
+f64 = lab.clone()
+torch.cuda.synchronize()
+e0, e1 = ev(), ev()
+e0.record()
+ops.bcd(pv, lc, npr, f64, sweeps, mode=lib.BCD_FP64_F32COST)
+e1.record()
+torch.cuda.synchronize()
+print(json.dumps({"fp64_ksets_total_ms": round(e0.elapsed_time(e1), 3), "sweeps": sweeps}))
