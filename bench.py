@@ -12,8 +12,13 @@ weak scaling, no data-path collective; value = N pairs / max-over-ranks time.
 value  : device-resident (images already in HBM), CUDA events, max over ranks.
 e2e    : the same through the host-buffer C ABI (flowb200_ctx_flow_pair_host): pinned H2D of both images,
          D2H of the checked field, inside the timed region.
-roofline: the dominant stage, algorithmic bytes/FLOPs / its CUDA-event time measured here.
+roofline: the dominant KERNEL (kset_chain32_kernel, one launch per BCD phase): algorithmic bytes per launch
+         / its own CUDA-event duration measured here phase by phase; the stage times and fractions are beside it.
 cpu_baseline: the CPU oracle (oracle/, C + numpy, all host threads) on a bounded crop of the same workload.
+huge   : (unless --no-huge) a short run of the single-huge-image mode (configs[4], 3840x2160, huge.py) on the same
+         ranks: ms per pair, and whether the sharded result is bit-identical to one GPU's.
+--workload 99pairs_...: configs[3] as written: 99 distinct host-resident pairs dealt round robin over the ranks
+         (dist.shard_units), each rank's share through flowb200_ctx_flow_pairs_host (copies overlapped).
 --impl reference: the CPU oracle alone, same metric/config (the reference itself is pure Python that
          needs opencv-contrib + pyflann, absent offline; its unmodified source runs only on tiny crops).
 """
@@ -50,7 +55,10 @@ WORKLOADS = {
     # configs[4]: ONE pair on all ranks, target cells sharded, NCCL merge (huge.py); strong scaling
     "3840x2160_huge_K150_bcd4": (2160, 3840, 150, 4, 2),
     "1920x1080_huge_K150_bcd4": (1080, 1920, 150, 4, 2),
+    # configs[3]: 99 pairs x 2 directions dealt over the ranks, host buffers in, host fields out
+    "99pairs_1024x436_fwdbwd_K300_bcd4": (436, 1024, 300, 4, 2),
 }
+HUGE_IN_BENCH = "3840x2160_huge_K150_bcd4"
 DEFAULT_WORKLOAD = "1024x436_fwdbwd_K300_bcd4"
 METRIC = "flow Mpix/s (DAISY+kNN+BCD+consistency)"
 
@@ -167,6 +175,39 @@ def stage_breakdown(ops, lib, p, sweeps, directions, g0, g1, bcd_mode, reps=2):
     return {k: v / reps for k, v in acc.items()}
 
 
+def chain_kernel_times(ops, lib, p, sweeps, g0, g1, reps=2):
+    """CUDA-event duration of every launch of the dominant kernel: flowb200_bcd_prepare (kset_sort + kset_build) and then
+    flowb200_bcd_phase once per phase (kset_chain32_kernel; the generic kernel launched behind it returns at once when no
+    chain is flagged), on the forward direction of one pair.  flowb200_bcd is exactly this sequence."""
+    import torch
+    d0, d1 = ops.daisy(g0), ops.daisy(g1)
+    pv, lc, npr, lab = ops.knn_proposals(d0, d1, p)
+    ops.random_proposals(d0, d1, p, pv, lc, npr, lab, seed=0)
+    ws = ops.bcd_workspace(pv)
+    kw = dict(mode=lib.BCD_INT32_F32COST, lamda=p.lamda, tpsi=p.tpsi, cost_shift=p.cost_shift)
+    prep, col, row = [], [], []
+    for rep in range(reps + 1):
+        l2 = lab.clone()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 + 4 * sweeps)]
+        torch.cuda.synchronize()
+        ev[0].record()
+        ops.bcd_prepare(pv, lc, npr, ws, 0, 1, **kw)
+        ev[1].record()
+        for w in range(sweeps):
+            for ph in range(4):
+                ops.bcd_phase(pv, lc, npr, l2, ws, ph, 0, 1, **kw)
+                ev[2 + 4 * w + ph].record()
+        torch.cuda.synchronize()
+        if rep == 0:
+            continue                               # warm-up
+        t = [ev[i].elapsed_time(ev[i + 1]) for i in range(len(ev) - 1)]
+        prep.append(t[0])
+        col += [t[1 + 4 * w + ph] for w in range(sweeps) for ph in (0, 2)]
+        row += [t[1 + 4 * w + ph] for w in range(sweeps) for ph in (1, 3)]
+    return {"prepare_ms": float(np.mean(prep)), "column_phase_ms": float(np.mean(col)), "row_phase_ms": float(np.mean(row)),
+            "ms_per_launch": float(np.mean(col + row))}
+
+
 def cpu_oracle_pipeline(img1, img2, op, sweeps, directions, con_tresh, seed=0):
     """The whole path on the CPU oracle (numpy DAISY + C generisi/nasumicni/BCD/consistency)."""
     from oracle import consistency as ocons, cport, daisy as od, proposals as oprop
@@ -204,7 +245,21 @@ def cpu_sample(p, sweeps, directions, steps=1):
         cpu_oracle_pipeline(img1, img2, op, sweeps, directions, p.con_tresh, seed=s)
         ts.append(time.perf_counter() - t0)
     t = float(np.mean(ts))
+
+    def cells_per_pixel(H, W):
+        tot = 0
+        for ci in range(W // p.cellw):
+            bw = min(W, p.cellw * (ci + p.cell_radius + 1)) - max(0, p.cellw * (ci - p.cell_radius))
+            for cj in range(H // p.cellh):
+                tot += bw * (min(H, p.cellh * (cj + p.cell_radius + 1)) - max(0, p.cellh * (cj - p.cell_radius)))
+        return tot / float(H * W)
+    c_crop, c_full = cells_per_pixel(Hs, Ws), cells_per_pixel(p.H, p.W)
     return {"value": Hs * Ws / 1e6 / t, "unit": "Mpix/s", "cores": cport.num_threads(), "kind": "port",
+            "crop": True, "extrapolated": False,
+            "cells_in_range_per_pixel": {"crop": round(c_crop, 2), "workload": round(c_full, 2)},
+            "note": "Mpix/s of the crop itself, not extrapolated: a pixel of the full workload searches "
+                    f"{c_full:.1f} cells on average against {c_crop:.1f} in the crop, so the full-size CPU figure would "
+                    "be lower (the exact search is ~60 % of the CPU time)",
             "sample": f"{steps} x {Ws}x{Hs} crop (5x5 cells of {p.cellw}x{p.cellh}), K={p.maxnprop}, bcd_times={sweeps}, "
                       f"{directions} direction(s), {t:.2f} s/step; C oracle with OpenMP + numpy DAISY",
             "seconds_per_step": t}
@@ -224,7 +279,8 @@ def run_reference(args):
                        "n_gauss": p.n_gauss, "bcd_times": sweeps, "directions": directions,
                        "parallelism": "CPU oracle on rank 0, all host threads; every step is the bounded sample "
                                       "named in cpu_baseline.sample"},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "crop", "extrapolated",
+                                               "cells_in_range_per_pixel", "note")},
             "e2e": {"value": r["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -326,6 +382,125 @@ def run_huge(args):
         dist.destroy_process_group()
 
 
+def huge_extra(rank, world, local, steps=2):
+    """Single-huge-image mode on the ranks of this run (the NCCL data plane the pair-sharded benchmark does not have):
+    ms per 3840x2160 pair (max over ranks), and whether the sharded result equals one GPU's bit for bit."""
+    import torch
+    import torch.distributed as dist
+    lib, ops, synth, huge = mod("_lib"), mod("ops"), mod("synth"), mod("huge")
+    p, sweeps, directions = make_params(HUGE_IN_BENCH, mod("params").DEFAULT_KNN_MODE)
+    a, b, _, _ = synth.make_pair(p.H, p.W, 0)
+    g0, g1 = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    D = dist if world > 1 else None
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    out = huge.flow_pair_sharded(g0, g1, p, sweeps, directions, 0, lib.BCD_INT32, rank, world, D)      # warm-up
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        out = huge.flow_pair_sharded(g0, g1, p, sweeps, directions, 1 + i, lib.BCD_INT32, rank, world, D)
+    e1.record()
+    sync()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    equal = None
+    if world > 1:      # the same pair and seed on this rank's GPU alone
+        want = ops.flow_pair(g0, g1, p, sweeps, directions, seed=steps, bcd_mode=lib.BCD_INT32)
+        ok = torch.tensor([1.0 if torch.equal(out, want) else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        equal = bool(ok.item() == 1.0)
+    return {"workload": HUGE_IN_BENCH, "ms_per_pair": float(t.item()), "mpix_per_s": p.H * p.W / 1e6 / (float(t.item()) / 1e3),
+            "n_gpus": world, "steps": steps, "scaling": "strong", "bit_equal_to_single_gpu": equal,
+            "exchange": "target cell columns sharded: one all-gather of packed slot ranges per direction; BCD chains of "
+                        "every phase split: one all-reduce of label differences per phase (huge.py)"}
+
+
+def run_batch(args):
+    """configs[3] as written: 99 distinct host-resident pairs x 2 directions, dealt round robin over the ranks
+    (dist.shard_units), every rank's share through flowb200_ctx_flow_pairs_host (host buffers in, host fields out,
+    the copies of pair i+1 / result i-1 overlapped with the computation of pair i).  value = 99 pairs / max-over-ranks
+    wall time of one pass over the share; steps = passes."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    lib, ops, synth, dm = mod("_lib"), mod("ops"), mod("synth"), mod("dist")
+    L = lib.load()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    p, sweeps, directions = make_params(args.workload, mod("params").DEFAULT_KNN_MODE)
+    n_pairs = 99
+    mine = dm.shard_units(n_pairs, rank, world)
+    # distinct pairs: picindex 0..98 (README.md:8) -> synthetic pair of that number
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, (os.cpu_count() or 8) // max(1, world))) as ex:   # (scipy releases the GIL)
+        pairs = list(ex.map(lambda i: synth.make_pair(p.H, p.W, i)[:2], mine))
+    outs = [np.empty((p.H, p.W, 3), dtype=np.float32) for _ in mine]
+    cp = ops.cparams(p, bcd_mode=lib.BCD_INT32)
+    ctx = L.flowb200_ctx_create(C.byref(cp))
+    if not ctx:
+        raise RuntimeError("flowb200_ctx_create failed: " + L.flowb200_last_cuda_error().decode())
+    PtrArr = C.c_void_p * len(mine)
+    a0 = PtrArr(*[a.ctypes.data for a, _ in pairs])
+    a1 = PtrArr(*[b.ctypes.data for _, b in pairs])
+    ao = PtrArr(*[o.ctypes.data for o in outs])
+
+    def one_pass(seed0):
+        lib.check(L.flowb200_ctx_flow_pairs_host(ctx, a0, a1, len(mine), sweeps, directions, seed0, ao),
+                  "flowb200_ctx_flow_pairs_host")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    lib.check(L.flowb200_ctx_flow_pairs_host(ctx, a0, a1, min(3, len(mine)), sweeps, directions, 0, ao), "warm-up")
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L0 = L.flowb200_launch_count()
+    t0 = time.perf_counter()
+    for s_ in range(args.steps):
+        one_pass(1000 * s_)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    launches = L.flowb200_launch_count() - L0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    tmin = t.clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    L.flowb200_ctx_destroy(ctx)
+    secs = float(t.item())
+    if rank == 0:
+        val = n_pairs * p.H * p.W / 1e6 / secs
+        emit({"metric": METRIC, "value": val, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": 1,
+              "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+              "dtype": "int32", "data": "synthetic", "pairs_per_s": n_pairs / secs,
+              "config": {"workload": args.workload, "H": p.H, "W": p.W, "K": p.maxnprop, "k_cell": p.k_cell,
+                         "n_gauss": p.n_gauss, "bcd_times": sweeps, "directions": directions, "pairs": n_pairs,
+                         "pairs_per_rank": [len(dm.shard_units(n_pairs, r, world)) for r in range(world)],
+                         "parallelism": f"99 pairs dealt round robin over {world} rank(s), no collective on the data path",
+                         "l2": "every pair is distinct; per-pair working set (>1 GB) exceeds L2",
+                         "timing": "wall clock around the blocking host API (a step = one pass over the 99 pairs), max over "
+                                   "ranks; the fastest rank needed %.3f s" % float(tmin.item())},
+              "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": n_pairs * 2 * p.H * p.W * 3,
+                      "d2h_bytes_per_step": n_pairs * p.H * p.W * 12},
+              "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -340,11 +515,14 @@ def main():
                          "each; pairs are independent, README.md:40).  1 = one pair after the other (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--no-huge", action="store_true", help="skip the short single-huge-image run (key 'huge')")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if "huge" in args.workload:
         return run_huge(args)
+    if args.workload.startswith("99pairs"):
+        return run_batch(args)
 
     import ctypes as C
     import torch
@@ -462,6 +640,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_mpix = world * p.H * p.W / 1e6 / (float(t.item()) / args.steps)
     L.flowb200_ctx_destroy(ctx)
+    huge_res = None
+    if not args.no_huge and args.workload == DEFAULT_WORKLOAD:
+        del ws
+        torch.cuda.empty_cache()
+        huge_res = huge_extra(rank, world, local)
+        ws = ops.pair_workspace(p, "cuda", bcd_mode)
 
     if rank == 0:
         pk = peaks()
@@ -469,32 +653,30 @@ def main():
         roof, stages = None, None
         if not args.no_breakdown:
             stages = stage_breakdown(ops, lib, p, sweeps, directions, dev_pairs[0][0], dev_pairs[0][1], bcd_mode)
-            dom = max(stages, key=stages.get)
-            kind, amount = work[dom]
-            secs = stages[dom] / 1e3
-            if kind == "hbm":
-                ach, peak, unit = amount / secs / 1e9, pk["hbm"], "GB/s"
-            else:
-                ach, peak, unit = amount / secs / 1e12, pk["tensor"], "TFLOP/s"
-            # per launch, as the contract asks: the dominant stage is a sequence of identical launches
-            n_launch = {"bcd": directions * sweeps * 4, "knn": directions, "daisy": 2, "random": directions,
-                        "consistency": 1}[dom]
-            kname = {"bcd": "kset_chain_kernel", "knn": "knn_select_kernel (+ re-rank)", "daisy": "daisy kernels",
-                     "random": "random_proposals_kernel", "consistency": "consistency_kernel"}[dom]
-            traffic = None
-            tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+            kt = chain_kernel_times(ops, lib, p, sweeps, dev_pairs[0][0], dev_pairs[0][1])
+            # the dominant kernel: kset_chain32_kernel, one launch per BCD phase.  Algorithmic bytes per launch =
+            # N * (8 K + 12) (2 N (8 K + 12) per sweep, every pixel visited once by a column and once by a
+            # row phase, i.e. half of the pixels per phase x 2 ... = a quarter of a sweep per launch)
+            n_launch = directions * sweeps * 4
+            per_launch = work["bcd"][1] / n_launch
+            ach = per_launch / (kt["ms_per_launch"] / 1e3) / 1e9
+            traffic, tsrc = None, None
+            tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
             if os.path.isfile(tpath):
                 with open(tpath) as f:
-                    for k, v in json.load(f)["kernels"].items():
-                        if k.startswith(kname.split(" ")[0]):
-                            traffic = v["mean_dram_bytes_per_launch"]
-            roof = {"kernel": kname, "stage": dom, "bound": kind, "achieved": ach, "peak": peak, "unit": unit,
-                    "frac": ach / peak, "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu --set full)",
+                    tj = json.load(f)
+                traffic = tj["kernels"].get("kset_chain32_kernel", {}).get("mean_dram_bytes_per_launch")
+                tsrc = "profiles/r02_traffic.json: " + tj.get("source", "")
+            roof = {"kernel": "kset_chain32_kernel", "stage": "bcd", "bound": "hbm", "achieved": ach, "peak": pk["hbm"],
+                    "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": traffic, "traffic_source": tsrc,
                     "peak_source": pk["src"] + " (MEASURED_PEAKS.json)", "launches_per_step": n_launch,
-                    "algorithmic_per_launch": amount / n_launch, "ms_per_launch": stages[dom] / n_launch,
-                    "note": "stage time by CUDA events around the stage's C-ABI call on the launching stream"
-                            + ("; includes kset_sort_kernel and kset_build_kernel once per direction" if dom == "bcd" else ""),
+                    "algorithmic_per_launch": per_launch, "ms_per_launch": kt["ms_per_launch"],
+                    "kernel_ms": {k: round(v, 4) for k, v in kt.items()},
+                    "note": "ms_per_launch = CUDA events around every flowb200_bcd_phase call of one direction run alone "
+                            "(column and row phases averaged); the kernel is bound by instruction issue and step "
+                            "latency, not by HBM (DESIGN.md 4.4)",
                     "stage_ms": {k: round(v, 4) for k, v in stages.items()},
+                    "stage_note": "stage = the stage's C-ABI calls of both directions one after the other, CUDA events",
                     "stage_frac_of_roofline": {
                         k: round((work[k][1] / (v / 1e3) / (1e9 if work[k][0] == "hbm" else 1e12)) /
                                  (pk["hbm"] if work[k][0] == "hbm" else pk["tensor"]), 5) if v > 0 else None
@@ -511,7 +693,8 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             r = cpu_sample(p, sweeps, directions, steps=2)
-            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "crop", "extrapolated",
+                                     "cells_in_range_per_pixel", "note")}
         line = {"metric": METRIC, "value": mpix, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": W_,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32" if bcd_mode == lib.BCD_INT32 else "f64", "data": "synthetic",
@@ -524,7 +707,7 @@ def main():
                 "e2e": {"value": e2e_mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * p.H * p.W * 3,
                         "d2h_bytes_per_step": p.H * p.W * 12},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "accuracy": accuracy}
+                "accuracy": accuracy, "huge": huge_res}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -204,6 +204,12 @@ void flowb200_ctx_destroy(flowb200_ctx* ctx);
  * Copies in, runs flowb200_flow_pair, copies out, synchronises. */
 int flowb200_ctx_flow_pair_host(flowb200_ctx* ctx, const uint8_t* bgr0_host, const uint8_t* bgr1_host,
                                 int sweeps, int directions, uint64_t seed, float* out_fwd_host);
+/* A batch of host-resident pairs, e.g. one rank's share of the 99 pairs x 2 directions of BASELINE.json configs[3]
+ * (README.md:8, :40: pairs are independent).  Pair i of bgr0_host[] / bgr1_host[] -> out_fwd_host[i], seed seed0 + i;
+ * the host<->device copies of the neighbouring pairs overlap the computation of pair i (second stream, two buffer
+ * sets).  Synchronises. */
+int flowb200_ctx_flow_pairs_host(flowb200_ctx* ctx, const uint8_t* const* bgr0_host, const uint8_t* const* bgr1_host,
+                                 int n_pairs, int sweeps, int directions, uint64_t seed0, float* const* out_fwd_host);
 /* postprocessing.fowardBackwardConsistency on host arrays (flow1_host modified in place). */
 int flowb200_consistency_host(float* flow1_host, const float* flow2_host, int A, int B, float tresh,
                               int a0, int a1, int b0, int b1);

@@ -65,6 +65,7 @@ SYMBOLS = {
     "flowb200_ctx_create": (_P, [_PP]),
     "flowb200_ctx_destroy": (None, [_P]),
     "flowb200_ctx_flow_pair_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_uint64, _P]),
+    "flowb200_ctx_flow_pairs_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_uint64, _P]),
     "flowb200_consistency_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]),
     "flowb200_remove_small_segments_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_int]),
     "flowb200_canny_edges_host": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

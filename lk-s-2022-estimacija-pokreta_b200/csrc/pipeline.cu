@@ -3,7 +3,9 @@
 // direction) + postprocessing.postProcessing compute between them, without the .npy round trips.
 // Also: error strings and the host-buffer context used by the drop-in scripts and the e2e benchmark.
 #include <atomic>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -18,25 +20,48 @@ void set_cuda_error(cudaError_t e, const char* where) {
 static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-// one auxiliary stream (+ fork/join events) per device and host thread, created on first use
+// Auxiliary streams (+ fork/join events) for the backward direction: a process-wide pool per device.  A call takes one
+// for its duration and gives it back, so that concurrent calls from any number of host threads (bench.py --inflight)
+// reuse a handful of streams instead of creating one per thread; they live until the process ends.
 struct AuxStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
 };
-static AuxStream* aux_stream() {
-  static thread_local AuxStream table[64];
+struct AuxPool {
+  std::mutex m;
+  std::vector<AuxStream*> idle[64];
+};
+static AuxPool& aux_pool() {
+  static AuxPool* p = new AuxPool();   // (never destroyed: CUDA may already be shut down at static destruction)
+  return *p;
+}
+static AuxStream* aux_acquire(int* dev_out) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  AuxStream* a = &table[dev];
-  if (!a->stream) {
-    if (cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&a->fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&a->join, cudaEventDisableTiming) != cudaSuccess) {
-      a->stream = nullptr;
-      return nullptr;
+  *dev_out = dev;
+  {
+    std::lock_guard<std::mutex> lock(aux_pool().m);
+    auto& v = aux_pool().idle[dev];
+    if (!v.empty()) {
+      AuxStream* a = v.back();
+      v.pop_back();
+      return a;
     }
   }
+  AuxStream* a = new AuxStream();
+  if (cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&a->fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&a->join, cudaEventDisableTiming) != cudaSuccess) {
+    if (a->stream) cudaStreamDestroy(a->stream);
+    if (a->fork) cudaEventDestroy(a->fork);
+    delete a;
+    return nullptr;
+  }
   return a;
+}
+static void aux_release(int dev, AuxStream* a) {
+  std::lock_guard<std::mutex> lock(aux_pool().m);
+  aux_pool().idle[dev].push_back(a);
 }
 
 struct PairLayout {
@@ -138,21 +163,33 @@ extern "C" int flowb200_flow_pair(const uint8_t* bgr0, const uint8_t* bgr1, cons
   // forward and backward are independent (README.md:40): the backward direction runs on an auxiliary stream
   // so that the small launches of one direction (BCD row phases have only H/2 chains) fill the SMs the other
   // leaves idle.  fork: aux waits for the DAISYs; join: `stream` waits for aux before the consistency check.
-  AuxStream* aux = directions == 2 ? aux_stream() : nullptr;
+  int aux_dev = 0;
+  AuxStream* aux = directions == 2 ? aux_acquire(&aux_dev) : nullptr;
   if (aux) {
-    FB_CUDA_CHECK(cudaEventRecord(aux->fork, stream));
-    FB_CUDA_CHECK(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
-    rc = run_direction(p, L, ws, 1, sweeps, seed, aux->stream);
+    // whatever happens after the fork, `stream` waits for the auxiliary stream before this call returns: the caller
+    // may reuse the workspace as soon as `stream` is done
+    cudaError_t e = cudaEventRecord(aux->fork, stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(aux->stream, aux->fork, 0);
+    int rc1 = FLOWB200_OK, rc0 = FLOWB200_OK;
+    if (e == cudaSuccess) {
+      rc1 = run_direction(p, L, ws, 1, sweeps, seed, aux->stream);
+      rc0 = run_direction(p, L, ws, 0, sweeps, seed, stream);
+      e = cudaEventRecord(aux->join, aux->stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, aux->join, 0);
+    }
+    aux_release(aux_dev, aux);
+    if (e != cudaSuccess) {
+      set_cuda_error(e, "flowb200_flow_pair (fork / join of the backward direction)");
+      return FLOWB200_ECUDA;
+    }
+    if (rc0 || rc1) return rc0 ? rc0 : rc1;
+  } else {
+    rc = run_direction(p, L, ws, 0, sweeps, seed, stream);
     if (rc) return rc;
-    FB_CUDA_CHECK(cudaEventRecord(aux->join, aux->stream));
-  }
-  rc = run_direction(p, L, ws, 0, sweeps, seed, stream);
-  if (rc) return rc;
-  if (aux) {
-    FB_CUDA_CHECK(cudaStreamWaitEvent(stream, aux->join, 0));
-  } else if (directions == 2) {
-    rc = run_direction(p, L, ws, 1, sweeps, seed, stream);
-    if (rc) return rc;
+    if (directions == 2) {
+      rc = run_direction(p, L, ws, 1, sweeps, seed, stream);
+      if (rc) return rc;
+    }
   }
   const size_t fbytes = n * 3 * sizeof(float);
   FB_CUDA_CHECK(cudaMemcpyAsync(out_fwd, ws + L.uvv[0], fbytes, cudaMemcpyDeviceToDevice, stream));
@@ -179,6 +216,14 @@ struct flowb200_ctx {
   float* d_out = nullptr;
   uint8_t* h_img[2] = {nullptr, nullptr};   // pinned staging
   float* h_out = nullptr;
+  // second set of image / output buffers, a copy stream and events: flowb200_ctx_flow_pairs_host moves pair i+1 in
+  // and result i-1 out while pair i is computed (created on first use)
+  cudaStream_t copy = nullptr;
+  uint8_t* d_img2[2] = {nullptr, nullptr};
+  float* d_out2 = nullptr;
+  uint8_t* h_img2[2] = {nullptr, nullptr};
+  float* h_out2 = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
 
 extern "C" void flowb200_ctx_destroy(flowb200_ctx* c) {
@@ -191,6 +236,19 @@ extern "C" void flowb200_ctx_destroy(flowb200_ctx* c) {
   cudaFreeHost(c->h_img[0]);
   cudaFreeHost(c->h_img[1]);
   cudaFreeHost(c->h_out);
+  if (c->copy) cudaStreamSynchronize(c->copy);
+  cudaFree(c->d_img2[0]);
+  cudaFree(c->d_img2[1]);
+  cudaFree(c->d_out2);
+  cudaFreeHost(c->h_img2[0]);
+  cudaFreeHost(c->h_img2[1]);
+  cudaFreeHost(c->h_out2);
+  for (int i = 0; i < 2; ++i) {
+    if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+  }
+  if (c->copy) cudaStreamDestroy(c->copy);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -237,6 +295,70 @@ extern "C" int flowb200_ctx_flow_pair_host(flowb200_ctx* c, const uint8_t* bgr0_
   FB_CUDA_CHECK(cudaMemcpyAsync(c->h_out, c->d_out, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   FB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   memcpy(out_fwd_host, c->h_out, n * 3 * sizeof(float));
+  return FLOWB200_OK;
+}
+
+// A batch of host-resident pairs (BASELINE.json configs[3]: a rank's share of the 99 pairs), one after the other on the
+// context's stream, with the copies of the neighbouring pairs overlapped: while pair i is computed, pair i+1 travels to
+// the device and result i-1 back, on a second stream (two buffer sets).
+extern "C" int flowb200_ctx_flow_pairs_host(flowb200_ctx* c, const uint8_t* const* bgr0_host, const uint8_t* const* bgr1_host,
+                                            int n_pairs, int sweeps, int directions, uint64_t seed0,
+                                            float* const* out_fwd_host) {
+  if (!c || !bgr0_host || !bgr1_host || !out_fwd_host || n_pairs < 0) return FLOWB200_EINVAL;
+  if (n_pairs == 0) return FLOWB200_OK;
+  const size_t n = (size_t)c->p.H * c->p.W, ibytes = n * 3, obytes = n * 3 * sizeof(float);
+  if (!c->copy) {   // second buffer set, copy stream, events
+    FB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      FB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->d_img2[i]), ibytes));
+      FB_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&c->h_img2[i]), ibytes, cudaHostAllocDefault));
+      FB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+      FB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+      FB_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+    }
+    FB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->d_out2), obytes));
+    FB_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&c->h_out2), obytes, cudaHostAllocDefault));
+  }
+  uint8_t* d_img[2][2] = {{c->d_img[0], c->d_img[1]}, {c->d_img2[0], c->d_img2[1]}};
+  uint8_t* h_img[2][2] = {{c->h_img[0], c->h_img[1]}, {c->h_img2[0], c->h_img2[1]}};
+  float* d_out[2] = {c->d_out, c->d_out2};
+  float* h_out[2] = {c->h_out, c->h_out2};
+  // pair i uses buffer set i & 1.  Copy stream, in this order: in(0), [in(i+1), out(i)] for every i.
+  auto copy_in = [&](int i) -> int {
+    const int s = i & 1;
+    if (i >= 2) FB_CUDA_CHECK(cudaEventSynchronize(c->ev_in[s]));   // staging buffer of pair i-2 has left the host
+    memcpy(h_img[s][0], bgr0_host[i], ibytes);
+    memcpy(h_img[s][1], bgr1_host[i], ibytes);
+    if (i >= 2) FB_CUDA_CHECK(cudaStreamWaitEvent(c->copy, c->ev_done[s], 0));   // pair i-2 no longer reads the images
+    FB_CUDA_CHECK(cudaMemcpyAsync(d_img[s][0], h_img[s][0], ibytes, cudaMemcpyHostToDevice, c->copy));
+    FB_CUDA_CHECK(cudaMemcpyAsync(d_img[s][1], h_img[s][1], ibytes, cudaMemcpyHostToDevice, c->copy));
+    FB_CUDA_CHECK(cudaEventRecord(c->ev_in[s], c->copy));
+    return FLOWB200_OK;
+  };
+  auto fetch_out = [&](int i) -> int {   // result i: pinned staging -> the caller's array
+    FB_CUDA_CHECK(cudaEventSynchronize(c->ev_out[i & 1]));
+    memcpy(out_fwd_host[i], h_out[i & 1], obytes);
+    return FLOWB200_OK;
+  };
+  int rc = copy_in(0);
+  if (rc) return rc;
+  for (int i = 0; i < n_pairs; ++i) {
+    const int s = i & 1;
+    if (i + 1 < n_pairs && (rc = copy_in(i + 1))) return rc;
+    FB_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_in[s], 0));
+    if (i >= 2) FB_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_out[s], 0));   // result i-2 has left d_out[s]
+    rc = flowb200_flow_pair(d_img[s][0], d_img[s][1], &c->p, sweeps, directions, seed0 + (uint64_t)i, d_out[s], nullptr,
+                            nullptr, c->ws, c->ws_bytes, c->stream);
+    if (rc) return rc;
+    FB_CUDA_CHECK(cudaEventRecord(c->ev_done[s], c->stream));
+    if (i >= 2 && (rc = fetch_out(i - 2))) return rc;             // frees h_out[s] for result i
+    FB_CUDA_CHECK(cudaStreamWaitEvent(c->copy, c->ev_done[s], 0));
+    FB_CUDA_CHECK(cudaMemcpyAsync(h_out[s], d_out[s], obytes, cudaMemcpyDeviceToHost, c->copy));
+    FB_CUDA_CHECK(cudaEventRecord(c->ev_out[s], c->copy));
+  }
+  for (int i = n_pairs >= 2 ? n_pairs - 2 : 0; i < n_pairs; ++i)
+    if ((rc = fetch_out(i))) return rc;
+  FB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   return FLOWB200_OK;
 }
 

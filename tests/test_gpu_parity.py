@@ -529,3 +529,34 @@ def test_bcd_in_pieces_equals_whole(nparts):
                 total += mine - labels
             labels = labels + total
         assert np.array_equal(labels.cpu().numpy(), z[f"labels{w + 1:02d}"]), w
+
+
+def test_ctx_batch_of_host_pairs_equals_single_calls():
+    """flowb200_ctx_flow_pairs_host (a rank's share of BASELINE configs[3], copies overlapped with the computation) returns,
+    for every pair, exactly what flowb200_ctx_flow_pair_host returns for it with the same seed."""
+    import ctypes as C
+    ops, lib, synth, params = pkg("ops"), pkg("_lib"), pkg("synth"), pkg("params")
+    L = lib.load()
+    H, W = 52, 70
+    p = params.FlowParams(H=H, W=W, cellw=16, cellh=12, n_gauss=10, maxnprop=140)
+    cp = ops.cparams(p, bcd_mode=lib.BCD_INT32)
+    ctx = L.flowb200_ctx_create(C.byref(cp))
+    assert ctx
+    try:
+        for n in (1, 2, 5):
+            pairs = [synth.make_pair(H, W, 20 + i, max_dx=5, max_dy=3, n_rect=1)[:2] for i in range(n)]
+            want = []
+            for i, (a, b) in enumerate(pairs):
+                o = np.empty((H, W, 3), np.float32)
+                lib.check(L.flowb200_ctx_flow_pair_host(ctx, a.ctypes.data, b.ctypes.data, 2, 2, 7 + i, o.ctypes.data), "single")
+                want.append(o)
+            outs = [np.full((H, W, 3), np.nan, np.float32) for _ in range(n)]
+            Arr = C.c_void_p * n
+            lib.check(L.flowb200_ctx_flow_pairs_host(ctx, Arr(*[a.ctypes.data for a, _ in pairs]),
+                                                     Arr(*[b.ctypes.data for _, b in pairs]), n, 2, 2, 7,
+                                                     Arr(*[o.ctypes.data for o in outs])), "batch")
+            for i in range(n):
+                assert np.array_equal(outs[i], want[i]), (n, i)
+        assert L.flowb200_ctx_flow_pairs_host(ctx, None, None, 0, 2, 2, 0, None) == lib.EINVAL
+    finally:
+        L.flowb200_ctx_destroy(ctx)
