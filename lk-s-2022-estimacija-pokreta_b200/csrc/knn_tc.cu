@@ -585,15 +585,22 @@ knn_rerank_kernel(const float* __restrict__ desc_src, const float* __restrict__ 
       const float lo1 = ds1 * (1.0f - 1.0e-5f), hi1 = ds1 * (1.0f + 1.0e-5f);
       int rank0 = 0, rank1 = 0;
       bool amb0 = false, amb1 = false;
-      for (int l = 0; l < 16; ++l) {
-        const float od = __shfl_sync(gmask, ds0, l, 16);
-        const float ol = od * (1.0f - 1.0e-5f), oh = od * (1.0f + 1.0e-5f);
-        rank0 += od < ds0;
-        amb0 |= (l != sub) && !(oh < lo0) && !(hi0 < ol);
-        rank1 += od < ds1;
-        amb1 |= !(oh < lo1) && !(hi1 < ol);
-      }
-      if (two) {
+      const int nl = n < 16 ? n : 16;   // (lanes >= n hold infinity: "certainly larger", they change nothing)
+      if (!two) {   // (uniform over the half-warp) the common case: one round, candidates 0..n-1
+        for (int l = 0; l < nl; ++l) {
+          const float ol = __shfl_sync(gmask, lo0, l, 16), oh = __shfl_sync(gmask, hi0, l, 16);
+          rank0 += oh < lo0;                                   // certainly smaller
+          amb0 |= (l != sub) && !(oh < lo0) && !(hi0 < ol);    // intervals overlap
+        }
+      } else {
+        for (int l = 0; l < 16; ++l) {
+          const float od = __shfl_sync(gmask, ds0, l, 16);
+          const float ol = od * (1.0f - 1.0e-5f), oh = od * (1.0f + 1.0e-5f);
+          rank0 += od < ds0;
+          amb0 |= (l != sub) && !(oh < lo0) && !(hi0 < ol);
+          rank1 += od < ds1;
+          amb1 |= !(oh < lo1) && !(hi1 < ol);
+        }
         for (int l = 0; l < 16; ++l) {
           const float od = __shfl_sync(gmask, ds1, l, 16);
           const float ol = od * (1.0f - 1.0e-5f), oh = od * (1.0f + 1.0e-5f);
