@@ -409,8 +409,10 @@ def huge_extra(rank, world, local, steps=2):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     equal = None
-    if world > 1:      # the same pair and seed on this rank's GPU alone
-        want = ops.flow_pair(g0, g1, p, sweeps, directions, seed=steps, bcd_mode=lib.BCD_INT32)
+    if world > 1:      # the same pair and seed on this rank's GPU alone (the same code as one part, no exchange:
+                       # flowb200_flow_pair's own workspace layout would not fit 180 GB at this size)
+        torch.cuda.empty_cache()
+        want = huge.flow_pair_sharded(g0, g1, p, sweeps, directions, steps, lib.BCD_INT32, 0, 1, None)
         ok = torch.tensor([1.0 if torch.equal(out, want) else 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         equal = bool(ok.item() == 1.0)
