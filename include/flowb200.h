@@ -69,6 +69,10 @@ typedef struct flowb200_params {
   int32_t bcd_mode;          /* FLOWB200_BCD_*                                */
   int32_t knn_mode;          /* FLOWB200_KNN_*                                */
   float con_tresh;           /* 10   README.md:65                             */
+  int32_t cell_x0, cell_x1;  /* target cell columns searched by flowb200_knn_proposals: [cell_x0, cell_x1);
+                                0, 0 = all.  For callers that shard the target cells (single-huge-image mode): the
+                                slots of the other columns' proposals are left unwritten, nprop / labels assume
+                                the full set.  Honoured by FLOWB200_KNN_TCGEN05 (KNN_EXACT_FP64 searches all). */
 } flowb200_params;
 
 int flowb200_version(void);

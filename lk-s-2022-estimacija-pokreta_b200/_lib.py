@@ -22,6 +22,7 @@ class CParams(C.Structure):
         ("cell_radius", C.c_int32), ("k_cell", C.c_int32), ("n_gauss", C.c_int32), ("sigma", C.c_float),
         ("maxnprop", C.c_int32), ("tphi", C.c_float), ("tpsi", C.c_int32), ("lamda", C.c_double),
         ("cost_shift", C.c_int32), ("bcd_mode", C.c_int32), ("knn_mode", C.c_int32), ("con_tresh", C.c_float),
+        ("cell_x0", C.c_int32), ("cell_x1", C.c_int32),
     ]
 
 

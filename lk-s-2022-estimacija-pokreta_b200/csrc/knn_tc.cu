@@ -69,6 +69,7 @@ constexpr float kPadNorm = 60000.0f;   // n_hi of padding target rows: their sco
 
 struct KnnTcGeom {
   int H, W, cellw, cellh, ncellx, ncelly, R, K, T, Tpad, stride_s, tiles_x, tiles_y, nblk;
+  int cx0, cx1;   // target cell columns searched (flowb200_params.cell_x0 / cell_x1; all: 0, ncellx)
   float tphi;
 };
 
@@ -220,6 +221,7 @@ __device__ __forceinline__ bool decode_item(const KnnTcGeom& g, int item, int& c
   cell = item - t * ncell;
   const int tyi = t / g.tiles_x, txi = t - tyi * g.tiles_x;
   const int ci = cell % g.ncellx, cj = cell / g.ncellx;
+  if (ci < g.cx0 || ci >= g.cx1) return false;   // not this caller's band of target cells
   const int x0 = max(0, g.cellw * (ci - g.R)), y0 = max(0, g.cellh * (cj - g.R));
   x1 = min(g.W, g.cellw * (ci + g.R + 1));
   y1 = min(g.H, g.cellh * (cj + g.R + 1));
@@ -550,6 +552,7 @@ knn_rerank_kernel(const float* __restrict__ desc_src, const float* __restrict__ 
   for (int ci = cimin; ci <= cimax; ++ci) {
     for (int cj = cjmin; cj <= cjmax; ++cj, ++blk) {
       const size_t task = pix * g.nblk + blk;
+      if (ci < g.cx0 || ci >= g.cx1) continue;   // (uniform over the half-warp) another caller's band: slots left unwritten
       const int n = cand_cnt[task];
       if (n == 255) {
         if (sub == 0) {
@@ -785,6 +788,12 @@ static KnnTcGeom make_tc_geom(const flowb200_params* p) {
   g.tiles_x = (min(g.W, r * g.cellw) + kTileW * kTilesPerItem - 1) / (kTileW * kTilesPerItem);
   g.tiles_y = (min(g.H, r * g.cellh) + kTileH - 1) / kTileH;
   g.nblk = r * r;
+  g.cx0 = 0;
+  g.cx1 = g.ncellx;
+  if (p->cell_x1 > p->cell_x0) {
+    g.cx0 = max(0, p->cell_x0);
+    g.cx1 = min(g.ncellx, p->cell_x1);
+  }
   return g;
 }
 

@@ -28,8 +28,8 @@ class Band:
     ci_hi: int
     sx0: int          # source columns [sx0, sx1) of the sub-image (sx0 is a multiple of cellw)
     sx1: int
-    tx0: int          # target columns of the sub-image = the same [sx0, sx1): cells outside the band are searched
-    tx1: int          # too (halo, wasted) and their slots ignored by the merge
+    tx0: int          # target columns of the sub-image = the same [sx0, sx1); only the band's cells are searched
+    tx1: int          # (FlowParams.cell_x0 / cell_x1), the other slots stay unwritten and the merge ignores them
 
     @property
     def width(self):
@@ -52,8 +52,12 @@ def band_plan(p: FlowParams, world: int):
 
 
 def sub_params(p: FlowParams, b: Band) -> FlowParams:
-    """Parameters of the rank's sub-image problem (full height, columns [sx0, sx1))."""
-    return p.with_shape(p.H, b.width)
+    """Parameters of the rank's sub-image problem (full height, columns [sx0, sx1)); only the band's own cell columns
+    are searched (the sub-image also holds up to cell_radius halo columns on either side, which the source pixels of
+    the band's edge need as SOURCES only)."""
+    from dataclasses import replace
+    c0 = b.ci_lo - b.sx0 // p.cellw
+    return replace(p.with_shape(p.H, b.width), cell_x0=c0, cell_x1=c0 + (b.ci_hi - b.ci_lo))
 
 
 def _row_groups(p: FlowParams):

@@ -41,7 +41,7 @@ def cparams(p: FlowParams, bcd_mode=_lib.BCD_FP64_F32COST, knn_mode=None):
     return _lib.CParams(H=p.H, W=p.W, cellw=p.cellw, cellh=p.cellh, cell_radius=p.cell_radius, k_cell=p.k_cell,
                         n_gauss=p.n_gauss, sigma=p.sigma, maxnprop=p.maxnprop, tphi=p.tphi, tpsi=p.tpsi,
                         lamda=p.lamda, cost_shift=p.cost_shift, bcd_mode=bcd_mode, knn_mode=knn_mode,
-                        con_tresh=p.con_tresh)
+                        con_tresh=p.con_tresh, cell_x0=p.cell_x0, cell_x1=p.cell_x1)
 
 
 def _workspace(nbytes, device):

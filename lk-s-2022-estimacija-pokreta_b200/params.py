@@ -29,6 +29,8 @@ class FlowParams:
     con_tresh: float = 10.0      # README.md:65
     cost_shift: int = 12         # S: int32 BCD works in units of 2^-S (costs quantised to 20*m/2^S)
     knn_mode: int = 0            # FLOWB200_KNN_* (0 = float64 CUDA cores, 1 = tcgen05 prefilter + exact re-rank)
+    cell_x0: int = 0             # target cell columns searched: [cell_x0, cell_x1); 0, 0 = all (huge.py: a rank's band)
+    cell_x1: int = 0
 
     @property
     def ncellx(self):
@@ -63,6 +65,8 @@ class FlowParams:
             raise ValueError("k_cell larger than a cell")
         if self.maxnprop > 512:
             raise ValueError("maxnprop > 512 not supported")
+        if (self.cell_x0, self.cell_x1) != (0, 0) and not 0 <= self.cell_x0 < self.cell_x1 <= self.ncellx:
+            raise ValueError("cell_x0 / cell_x1 must select a non-empty range of cell columns")
         return self
 
 
