@@ -156,9 +156,9 @@ __device__ __forceinline__ Ranges lookup_ranges(const uint32_t* rng, int32_t v, 
 
 // Shared memory of one build CTA (one record at a time):
 // rng u32[kHashSize] | hist u32[128] | start u32[128] | gstart u32[128] | misc u32[16] | vq2 int2[Kpad] |
-// kq3, ln, so, rk, inv, cq u16[Kpad] | stage u16[kStagePerLabel * Kpad]
+// ln, so, rk, inv, cq u16[Kpad] | stage u16[kStagePerLabel * Kpad]
 __host__ __device__ inline size_t build_smem_bytes(int Kpad) {
-  return (size_t)kHashSize * 4 + 128 * 4 * 3 + 64 + (size_t)Kpad * 8 + (size_t)Kpad * 2 * 6 +
+  return (size_t)kHashSize * 4 + 128 * 4 * 3 + 64 + (size_t)Kpad * 8 + (size_t)Kpad * 2 * 5 +
          (size_t)kStagePerLabel * Kpad * 2;
 }
 
@@ -183,9 +183,8 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
   uint32_t* gstart = start + 128;        // first entry group of the labels with list length m
   uint32_t* misc = gstart + 128;         // [0] staged entries, [1] failure flag, [3] ok, [4..5] arena offset,
                                          // [6] struct offset, [7] entry offset
-  int2* vq2 = reinterpret_cast<int2*>(misc + 16);
-  uint16_t* kq3 = reinterpret_cast<uint16_t*>(vq2 + Kpad);
-  uint16_t* ln = kq3 + Kpad;
+  int2* vq2 = reinterpret_cast<int2*>(misc + 16);   // previous pixel's labels: {dy, dx << 16 | label << 3}: one 8-byte load
+  uint16_t* ln = reinterpret_cast<uint16_t*>(vq2 + Kpad);
   uint16_t* so = ln + Kpad;
   uint16_t* rk = so + Kpad;
   uint16_t* inv = rk + Kpad;
@@ -225,8 +224,7 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
       const int32_t* svq = svec + (size_t)q * Kst;
       for (int s = t; s < nq; s += kBuildThreads) {
         const int32_t v = svq[s];
-        vq2[s] = make_int2(vec_dy(v), vec_dx(v));
-        kq3[s] = (uint16_t)((uint32_t)sq[s] << 3);
+        vq2[s] = make_int2(vec_dy(v), (int)(((uint32_t)vec_dx(v) << 16) | ((uint32_t)sq[s] << 3)));
         inv[s] = (uint16_t)bucket_key(v, bshift);
       }
     }
@@ -286,8 +284,8 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
         for (uint32_t xx = 0; xx < c; ++xx) {   // the three ranges as one index space
           const int tt = (int)xx + (xx < c0 ? o0 : (xx < c01 ? o1 : o2));
           const int2 u = vq2[tt];
-          const int l1 = (int)__sad(dy, u.x, __sad(dx, u.y, 0u));
-          if (l1 < tpsi) e[m++] = (uint16_t)((uint32_t)kq3[tt] | ((uint32_t)l1 << 13));
+          const int l1 = (int)__sad(dy, u.x, __sad(dx, u.y >> 16, 0u));
+          if (l1 < tpsi) e[m++] = (uint16_t)(((uint32_t)u.y & 0xFFFFu) | ((uint32_t)l1 << 13));
         }
         if (m > (uint32_t)kMaxList) {
           misc[1] = 1;
@@ -962,6 +960,7 @@ __device__ __forceinline__ void chain32_body(const ChainArgs& a) {
         const uint2* eg = reinterpret_cast<const uint2*>(rec + hdr.w) + g0;
         const uint32_t base = rep_u32 | ((uint32_t)((i & 1) ^ 1) << 2);   // previous step's buffer
         uint32_t v0 = kInf, k0 = kInf, v1 = kInf, k1 = kInf;   // two independent running minima
+#pragma unroll 1
         for (uint32_t gi = 0; gi < ng; ++gi) {
           const uint2 w = eg[gi];
           // an entry: bits 3..11 = previous-pixel label << 3 (= offset of its dp pair), bits 13..15 = L1
