@@ -155,6 +155,12 @@ int flowb200_bcd_phase(const int32_t* pvec, const void* cost, const int32_t* npr
                        int K, int bcd_mode, double lamda, int tpsi, int cost_shift, int phase, int part, int nparts,
                        void* workspace, size_t workspace_bytes, flowb200_stream_t stream);
 
+/* bestlabels as generisi leaves them (daisy i flann.py:181-184): first strict minimum of the data costs of the first
+ * nprop slots (0 where nprop is 0).  flowb200_knn_proposals computes them itself; this entry point serves callers that
+ * assemble a proposal set from pieces (single-huge-image mode: the bands of several GPUs). */
+int flowb200_best_labels(const float* lcost, const int32_t* nprop, int H, int W, int K, int32_t* labels,
+                         flowb200_stream_t stream);
+
 /* ---- A5  vratiKonacniFlow (daisy i flann.py:192-197) + A12 FlowImage.ucitajFlow (postprocessing.py:7-17) ----
  * flow_yx (optional): float64 [H][W][2] = (dy,dx);  uvv (optional): float32 [H][W][3] = (dx, dy, 1). */
 int flowb200_flow_from_labels(const int32_t* pvec, const int32_t* labels, int H, int W, int K,

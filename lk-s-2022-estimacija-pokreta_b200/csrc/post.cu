@@ -101,6 +101,36 @@ extern "C" int flowb200_epe(const float* test_uvv, const float* gt_uvv, int H, i
   return FLOWB200_OK;
 }
 
+// bestlabels of generisi (daisy i flann.py:181-184): the first strict minimum of the data costs of the first nprop
+// slots.  One warp per pixel; costs are >= 0, so (float bits << 32 | slot) orders like (cost, slot).
+__global__ void best_labels_kernel(const float* __restrict__ lcost, const int32_t* __restrict__ nprop, int n, int K,
+                                   int32_t* __restrict__ labels) {
+  const int pix = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (pix >= n) return;
+  const int np = min(nprop[pix], K);
+  const float* c = lcost + (size_t)pix * K;
+  unsigned long long best = ~0ull;
+  for (int s = lane; s < np; s += 32) {
+    const unsigned long long key = ((unsigned long long)__float_as_uint(c[s]) << 32) | (uint32_t)s;
+    best = key < best ? key : best;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
+    best = o < best ? o : best;
+  }
+  if (lane == 0) labels[pix] = np > 0 ? (int32_t)(best & 0xffffffffu) : 0;
+}
+
+extern "C" int flowb200_best_labels(const float* lcost, const int32_t* nprop, int H, int W, int K, int32_t* labels,
+                                    flowb200_stream_t stream) {
+  if (!lcost || !nprop || !labels || H <= 0 || W <= 0 || K <= 0) return FLOWB200_EINVAL;
+  const int n = H * W;
+  best_labels_kernel<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, stream>>>(lcost, nprop, n, K, labels);
+  FB_LAUNCH_CHECK();
+  return FLOWB200_OK;
+}
+
 extern "C" int flowb200_flow_from_labels(const int32_t* pvec, const int32_t* labels, int H, int W, int K,
                                          double* flow_yx, float* uvv, flowb200_stream_t stream) {
   if (!pvec || !labels || H <= 0 || W <= 0 || K <= 0) return FLOWB200_EINVAL;

@@ -145,6 +145,20 @@ def unpack_band(p: FlowParams, b: Band, flat, pvec, lcost):
         o += cnt
 
 
+def _best_labels(lcost, nprop):
+    """bestlabels from the merged data costs: flowb200_best_labels on the device.  CPU tensors occur only in the gloo
+    tests of this module's host logic (tests/test_huge_plan.py); for them the same definition is evaluated with torch."""
+    import torch
+    if lcost.is_cuda:
+        from . import ops
+        return ops.best_labels(lcost, nprop)
+    K = lcost.shape[2]
+    key = (lcost.contiguous().view(torch.int32).to(torch.int64) << 32) | torch.arange(K, dtype=torch.int64)
+    key = torch.where(torch.arange(K)[None, None, :] < nprop[..., None], key, torch.full_like(key, 2 ** 62))
+    labels = (key.min(dim=2).values & 0xFFFFFFFF).to(torch.int32)
+    return torch.where(nprop > 0, labels, torch.zeros_like(labels))
+
+
 def merge_bands(p: FlowParams, bands, rank, sub_pvec, sub_lcost, device, dist=None, blocks=None):
     """Every rank contributes the slot ranges of its band (packed, no halo columns, no unused slots) to ONE all-gather;
     every rank unpacks all bands into the full proposal set.
@@ -180,13 +194,7 @@ def merge_bands(p: FlowParams, bands, rank, sub_pvec, sub_lcost, device, dist=No
         if sizes[b.rank]:
             unpack_band(p, b, recv[b.rank], pvec, lcost)
     nprop = torch.from_numpy(nn_counts(p)).to(device)
-    # first strict argmin: costs are >= 0, so the float bit pattern orders like the value; the slot breaks ties
-    labels = torch.empty((H, W), dtype=torch.int32, device=device)
-    slot = torch.arange(K, device=device, dtype=torch.int64)
-    for y0 in range(0, H, 128):   # row blocks bound the int64 temporary
-        key = (lcost[y0:y0 + 128].view(torch.int32).to(torch.int64) << 32) | slot
-        labels[y0:y0 + 128] = (key.min(dim=2).values & 0xFFFFFFFF).to(torch.int32)
-    labels = torch.where(nprop > 0, labels, torch.zeros_like(labels))
+    labels = _best_labels(lcost, nprop)       # first strict argmin of the data costs (daisy i flann.py:181-184)
     return pvec, lcost, nprop, labels
 
 
@@ -194,6 +202,8 @@ def knn_proposals_sharded(desc_src, desc_tgt, p: FlowParams, rank, world, dist=N
     """generisi for one direction with the target cells sharded over `world` ranks.  Same outputs as
     ops.knn_proposals on one device."""
     from . import ops
+    if world == 1:   # nothing to merge: the ordinary search
+        return ops.knn_proposals(desc_src, desc_tgt, p, knn_mode=knn_mode)
     bands = band_plan(p, world)
     b = bands[rank]
     sub_pvec = sub_lcost = None

@@ -175,6 +175,16 @@ def bcd_phase(pvec, cost, nprop, labels, ws, phase, part=0, nparts=1, mode=_lib.
                                       int(nparts), _ptr(ws), ws.numel(), _stream()), "flowb200_bcd_phase")
 
 
+def best_labels(lcost, nprop):
+    """bestlabels of generisi (daisy i flann.py:181-184) from the data costs: int32 (H,W)."""
+    lib = _lib.load()
+    H, W, K = lcost.shape
+    labels = torch.empty((H, W), dtype=torch.int32, device=lcost.device)
+    _lib.check(lib.flowb200_best_labels(_ptr(lcost, torch.float32, "lcost"), _ptr(nprop, torch.int32, "nprop"), H, W, K,
+                                        _ptr(labels), _stream()), "flowb200_best_labels")
+    return labels
+
+
 def flow_from_labels(pvec, labels, want_yx=True, want_uvv=True):
     """vratiKonacniFlow (+ FlowImage layout).  Returns (flow_yx float64 (H,W,2) | None, uvv float32 (H,W,3) | None)."""
     lib = _lib.load()

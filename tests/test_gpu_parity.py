@@ -560,3 +560,25 @@ def test_ctx_batch_of_host_pairs_equals_single_calls():
         assert L.flowb200_ctx_flow_pairs_host(ctx, None, None, 0, 2, 2, 0, None) == lib.EINVAL
     finally:
         L.flowb200_ctx_destroy(ctx)
+
+
+def test_best_labels_kernel():
+    """flowb200_best_labels = the first strict minimum of the first nprop data costs (daisy i flann.py:181-184), ties and
+    empty pixels included; on a real proposal set it reproduces the labels the search itself returns."""
+    ops, params, synth = pkg("ops"), pkg("params"), pkg("synth")
+    rng = np.random.default_rng(8)
+    H, W, K = 37, 53, 70
+    lc = rng.integers(0, 6, (H, W, K)).astype(np.float32) * 0.25          # many ties
+    npr = rng.integers(0, K + 1, (H, W)).astype(np.int32)
+    want = np.zeros((H, W), np.int32)
+    for y in range(H):
+        for x in range(W):
+            if npr[y, x]:
+                want[y, x] = int(np.argmin(lc[y, x, :npr[y, x]]))
+    got = ops.best_labels(dev(lc), dev(npr)).cpu().numpy()
+    assert np.array_equal(got, want)
+    p = params.FlowParams(H=61, W=90, cellw=16, cellh=12, n_gauss=0, maxnprop=125, knn_mode=1)
+    a, b, _, _ = synth.make_pair(61, 90, 5, max_dx=5, max_dy=3, n_rect=2)
+    d1, d2 = ops.daisy(dev(a)), ops.daisy(dev(b))
+    pv, lcost, nprop, labels = ops.knn_proposals(d1, d2, p)
+    assert torch.equal(ops.best_labels(lcost, nprop), labels)
