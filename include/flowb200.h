@@ -44,7 +44,8 @@ enum {
  *   FP64_F32COST / FP64_F64COST: float64 dynamic programme with the reference's operation order,
  *       bit-exact labels for arbitrary data costs (cost array float32 resp. float64);
  *   INT32: int32 dynamic programme in units of 2^-cost_shift on integer data costs m
- *       (lamda*lcost*2^S == m); bit-exact with the reference whenever lcost == 20*m/2^S;
+ *       (lamda*lcost*2^S == m, 0 <= m < 65536, 4 <= cost_shift <= 14); bit-exact with the reference whenever
+ *       lcost == 20*m/2^S;
  *   INT32_F32COST: the same int32 programme fed with float32 costs, m = rint(lamda*lcost*2^S) on the fly
  *       (what flowb200_quantise_costs computes, without the extra array). */
 enum { FLOWB200_BCD_FP64_F32COST = 0, FLOWB200_BCD_FP64_F64COST = 1, FLOWB200_BCD_INT32 = 2,

@@ -70,6 +70,7 @@ def quantised_m(lcosts, lamda, shift):
     used = a != 1000.0
     m = np.where(used, lamda * a * float(1 << shift), 0.0)
     r = np.rint(m)
-    if not np.array_equal(r, m) or r.max(initial=0) >= 2 ** 30:
+    # the int32 programme holds a data cost in 16 bits (include/flowb200.h: 0 <= m < 65536)
+    if not np.array_equal(r, m) or r.max(initial=0) >= 65536 or r.min(initial=0) < 0:
         return None
     return r.astype(np.int32)

@@ -101,6 +101,9 @@ def test_quantised_cost_detection():
     assert ioc.quantised_m(lq2, 0.05, 12) is None
     lq[0, 0, 7] = 1000.0
     assert ioc.quantised_m(lq, 0.05, 12)[0, 0, 7] == 0
+    # integral but outside the 16-bit data cost field of the int32 programme (or negative): not accepted
+    assert ioc.quantised_m(20.0 * np.array([[[70000.0]]]) / 4096.0, 0.05, 12) is None
+    assert ioc.quantised_m(20.0 * np.array([[[-3.0]]]) / 4096.0, 0.05, 12) is None
 
 
 def test_file_names_match_reference_contract():

@@ -57,3 +57,19 @@ def test_true_match_is_nearest():
     b = d2[23:43, 25:55]
     assert np.abs(a - b).sum(-1).max() < 1e-5
     assert np.abs(a - d2[20:40, 30:60]).sum(-1).mean() > 0.05
+
+
+def test_oracle_against_opencv_contrib_daisy_when_installed():
+    """The reference calls cv2.xfeatures2d.DAISY_create(radius=5, q_radius=4, q_theta=4, q_hist=4) (daisy i flann.py:66,
+    :69-77).  opencv-contrib is absent from this image (DAISY parity is "unpinned"); wherever it IS
+    installed this test pins the oracle against it at the north star's 1e-4 relative."""
+    if not hasattr(cv2, "xfeatures2d") or not hasattr(cv2.xfeatures2d, "DAISY_create"):
+        pytest.skip("opencv-contrib (cv2.xfeatures2d) is not installed")
+    img = _img(48, 64, 3)
+    daisy = cv2.xfeatures2d.DAISY_create(radius=5, q_radius=4, q_theta=4, q_hist=4)
+    kp = [cv2.KeyPoint(float(x), float(y), 1) for y in range(img.shape[0]) for x in range(img.shape[1])]
+    _, d = daisy.compute(img, kp)
+    want = np.asarray(d, np.float32).reshape(img.shape[0], img.shape[1], 68)
+    got = od.daisy(img)
+    scale = np.abs(want).max(axis=-1, keepdims=True) + 1e-12
+    assert (np.abs(got - want) / scale).max() <= 1e-4
