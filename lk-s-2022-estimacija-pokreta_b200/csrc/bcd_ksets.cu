@@ -438,10 +438,10 @@ __host__ __device__ inline uint32_t kset_slot_bytes(int Kpad) {
 __host__ __device__ inline size_t chain_fixed_smem(int Kpad, int len) {
   return (4 * (size_t)len + 4 * (size_t)Kpad + 2 * (size_t)len + 127) & ~(size_t)127;
 }
-// ... of the 32-bit kernel, behind the (run-time) pad that aligns it to 4 KB: keys 4 KB | oldvec int32[len] |
-// path uint16[len] | the record slots, 128-aligned
+// ... of the 32-bit kernel, behind the (run-time) pad that aligns it to 4 KB: dp 4 KB | control 384 B |
+// oldvec int32[len] | path uint16[len] | the record slots, 128-aligned
 __host__ __device__ inline size_t chain32_fixed_smem(int len) {
-  return (4096 + 4 * (size_t)len + 2 * (size_t)len + 127) & ~(size_t)127;
+  return (4096 + 384 + 4 * (size_t)len + 2 * (size_t)len + 127) & ~(size_t)127;
 }
 
 // backtrack (:238-253) through the back-pointers of the chain of this block, staged through shared memory (the record
@@ -861,15 +861,13 @@ __device__ __forceinline__ void chainf64_body(const ChainArgs& a) {
 // again: one column chain in 512 went wrong at 1024x436.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kKeyBytes = 4096;   // dp of labels 0..510 in two buffers; the slot of label 511 stays infinite (null entries)
+constexpr int kCtlBytes = 384;    // warp minima [2][16] x 2, four mbarriers
 
 template <typename CostT, int T, int SHIFT>
 __device__ __forceinline__ void chain32_body(const ChainArgs& a) {
   constexpr int NW = T / 32;
   constexpr uint32_t kInf = 0xFFFFFFFFu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint32_t wred_v[2][kMaxWarps];   // per warp: minimum dp of a step (infinite for warps without labels) ...
-  __shared__ uint32_t wred_l[2][kMaxWarps];   // ... and the lowest label that has it
-  __shared__ __align__(8) uint64_t mbar[4];
   __shared__ int absent_s;
 
   const ChainGeom g = chain_geom(a.phase, a.chain0 + (int)blockIdx.x, a.H, a.W);
@@ -880,12 +878,17 @@ __device__ __forceinline__ void chain32_body(const ChainArgs& a) {
   const unsigned long long* dsc = a.desc + (size_t)(a.phase & 1) * a.H * a.W;
   const int len = g.len;
 
-  // dynamic shared memory: [pad] dp (4 KB aligned) | oldvec | path | record slots
+  // dynamic shared memory: [pad] dp (4 KB aligned) | warp minima, mbarriers (kCtlBytes) | oldvec | path | record slots.
+  // Everything hangs off ONE base pointer held in a register (static shared arrays cost an address computation from
+  // the cluster CTA id at every use on sm_100).
   const uint32_t dyn0 = ptx::smem_u32(smem_raw);
   const uint32_t pad = (0u - dyn0) & (uint32_t)(kKeyBytes - 1);
   uint32_t* rep_s = reinterpret_cast<uint32_t*>(smem_raw + pad);   // [2 * k + parity]
   const uint32_t rep_u32 = dyn0 + pad;
-  int32_t* oldvec = reinterpret_cast<int32_t*>(smem_raw + pad + kKeyBytes);
+  uint32_t (*wred_v)[kMaxWarps] = reinterpret_cast<uint32_t (*)[kMaxWarps]>(smem_raw + pad + kKeyBytes);         // [2][16]: per warp,
+  uint32_t (*wred_l)[kMaxWarps] = reinterpret_cast<uint32_t (*)[kMaxWarps]>(smem_raw + pad + kKeyBytes + 128);   // min dp of a step and the lowest label that has it
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + pad + kKeyBytes + 256);                                // [4]
+  int32_t* oldvec = reinterpret_cast<int32_t*>(smem_raw + pad + kKeyBytes + kCtlBytes);
   uint16_t* path = reinterpret_cast<uint16_t*>(oldvec + len);
   unsigned char* slots = smem_raw + pad + chain32_fixed_smem(len);
   auto pixel = [&](int i) { return (g.sy + i * g.ystep) * a.W + (g.sx + i * g.xstep); };
