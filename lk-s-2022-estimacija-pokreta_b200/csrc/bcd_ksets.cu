@@ -4,7 +4,7 @@
 //
 //   kset_sort_kernel   per pixel: label indices (and vectors) ordered by the spatial-hash bucket of the flow vector
 //   kset_build_kernel  per (pixel, chain orientation): one RECORD = everything a chain step needs, contiguous (layout
-//                      at the kernel).  Only pairs with L1 < tpsi are stored, as uint16 entries (k << 3 | L1 << 13),
+//                      at the kernel).  Only pairs with L1 < tpsi are stored, as uint16 entries (k << 3 | L1 << 12),
 //                      labels ordered by decreasing list length, every list padded to whole groups of four entries.
 //                      Records are carved from an arena with one atomic cursor; a 64-bit descriptor per record
 //                      (offset | size) is the only index.  All (pixel, orientation) pairs are independent, so this
@@ -103,12 +103,12 @@ kset_sort_kernel(const int32_t* __restrict__ pvec, const int32_t* __restrict__ n
 //   [0,16)   uint32 n, number of entry groups, struct byte offset, entry byte offset
 //   [16,..)  uint16 goff[n, padded to 8]: first entry group of position t
 //   structs  n x {int32 vector; uint32 data cost (16) | original label (9) << 16 | entry groups (7) << 25}
-//   entries  groups of four uint16 (8 bytes, one shared-memory load): (k << 3) | (L1 << 13) = previous-pixel label k
+//   entries  groups of four uint16 (8 bytes, one shared-memory load): (k << 3) | (L1 << 12) = previous-pixel label k
 //            (original index; << 3 = byte offset of its key pair in the chain kernel) and L1(v_l, u_k) < tpsi; a list
 //            is padded to whole groups with kNullEntry.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxList = 124;                  // 31 groups of four
-constexpr uint32_t kNullEntry = 0x1FF8u;       // bit 12 = "no entry"; its label field is 511, whose key slot the 32-bit
+constexpr uint32_t kNullEntry = 0x8FF8u;       // bit 15 = "no entry"; its label field is 511, whose key slot the 32-bit
                                                // chain kernel keeps infinite (it runs proposal sets of K <= 511 labels)
 constexpr uint32_t kCostLimit16 = 1u << 16;    // data cost field: 16 bits
 constexpr int kStagePerLabel = 16;             // staging capacity of the build kernel: candidates per label of Kpad
@@ -285,7 +285,7 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
           const int tt = (int)xx + (xx < c0 ? o0 : (xx < c01 ? o1 : o2));
           const int2 u = vq2[tt];
           const int l1 = (int)__sad(dy, u.x, __sad(dx, u.y >> 16, 0u));
-          if (l1 < tpsi) e[m++] = (uint16_t)(((uint32_t)u.y & 0xFFFFu) | ((uint32_t)l1 << 13));
+          if (l1 < tpsi) e[m++] = (uint16_t)(((uint32_t)u.y & 0xFFFFu) | ((uint32_t)l1 << 12));
         }
         if (m > (uint32_t)kMaxList) {
           misc[1] = 1;
@@ -585,8 +585,8 @@ __device__ __forceinline__ void chain64_body(const ChainArgs& a) {
             const uint32_t e[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (!(e[j] & 0x1000u))   // (not a padding entry)
-                acc = key_min(acc, *reinterpret_cast<const Key*>(rpb + key_off64(e[j], prv_off)) + key_scaled(e[j] >> 13, shift));
+              if (!(e[j] & 0x8000u))   // (not a padding entry)
+                acc = key_min(acc, *reinterpret_cast<const Key*>(rpb + key_off64(e[j], prv_off)) + key_scaled((e[j] >> 12) & 7u, shift));
           }
           bp_row[orig] = (uint16_t)key_label(acc);
           key = next_key(acc, U, orig);
@@ -771,9 +771,9 @@ __device__ __forceinline__ void chainf64_body(const ChainArgs& a) {
             const uint32_t e[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (!(e[j] & 0x1000u)) {   // (not a padding entry)
+              if (!(e[j] & 0x8000u)) {   // (not a padding entry)
                 const int k = (int)((e[j] >> 3) & 511u);
-                const double cand = __dadd_rn(rep_s[2 * k + prv], (double)(e[j] >> 13));
+                const double cand = __dadd_rn(rep_s[2 * k + prv], (double)((e[j] >> 12) & 7u));
                 if (cand < best || (cand == best && k < arg)) {   // np.argmin: lowest k wins ties
                   best = cand;
                   arg = k;
@@ -966,12 +966,23 @@ __device__ __forceinline__ void chain32_body(const ChainArgs& a) {
 #pragma unroll 1
         for (uint32_t gi = 0; gi < ng; ++gi) {
           const uint2 w = eg[gi];
-          // an entry: bits 3..11 = previous-pixel label << 3 (= offset of its dp pair), bits 13..15 = L1
-          const uint32_t ka = w.x & 0xFF8u, kb = (w.x >> 16) & 0xFF8u, kc = w.y & 0xFF8u, kd = (w.y >> 16) & 0xFF8u;
-          const uint32_t ca = ptx::lds_u32(ka | base) + (((w.x >> 13) & 7u) << shift);
-          const uint32_t cb = ptx::lds_u32(kb | base) + ((w.x >> 29) << shift);
-          const uint32_t cc = ptx::lds_u32(kc | base) + (((w.y >> 13) & 7u) << shift);
-          const uint32_t cd = ptx::lds_u32(kd | base) + ((w.y >> 29) << shift);
+          // an entry: bits 3..11 = previous-pixel label << 3 (= offset of its dp pair), bits 12..14 = L1 (with the usual
+          // shift of 12 the pairwise cost L1 << 12 is one mask of the entry)
+          const uint32_t hx = w.x >> 16, hy = w.y >> 16;
+          const uint32_t ka = w.x & 0xFF8u, kb = hx & 0xFF8u, kc = w.y & 0xFF8u, kd = hy & 0xFF8u;
+          uint32_t ca = ptx::lds_u32(ka | base), cb = ptx::lds_u32(kb | base);
+          uint32_t cc = ptx::lds_u32(kc | base), cd = ptx::lds_u32(kd | base);
+          if constexpr (SHIFT == 12) {
+            ca += w.x & 0x7000u;
+            cb += hx & 0x7000u;
+            cc += w.y & 0x7000u;
+            cd += hy & 0x7000u;
+          } else {
+            ca += ((w.x >> 12) & 7u) << shift;
+            cb += ((hx >> 12) & 7u) << shift;
+            cc += ((w.y >> 12) & 7u) << shift;
+            cd += ((hy >> 12) & 7u) << shift;
+          }
           lex_min(v0, k0, ca, ka);
           lex_min(v1, k1, cb, kb);
           lex_min(v0, k0, cc, kc);
