@@ -1092,10 +1092,12 @@ static inline void owned_chains(int phase, int H, int W, int part, int nparts, i
 template <typename CostT>
 struct KsetPlan {
   KsetLayout L;
-  void (*kern32)(const ChainArgs) = nullptr;   // every chain, 32-bit saturating keys
+  void (*kern32)(const ChainArgs) = nullptr;   // every chain, 32-bit dp
+  void (*kern32_lo)(const ChainArgs) = nullptr;  // the same compiled for one chain per SM fewer (more registers): used
+                                                 // for the orientation whose shared memory does not admit more anyway
   void (*kern64)(const ChainArgs) = nullptr;   // the chains the first could not certify
   void (*kernf64)(const ChainArgs) = nullptr;  // the float64 programme (every chain)
-  int T = 0, bshift = 0, slot_shift = 2;
+  int T = 0, bshift = 0, slot_shift = 2, minb = 1;
   uint32_t slot_bytes = 0;
   size_t smem32[2] = {0, 0}, smem64 = 0;   // smem32: by chain orientation (column chains are H long, row chains W)
 };
@@ -1118,6 +1120,9 @@ static int make_plan(int H, int W, int K, int tpsi, int shift, size_t workspace_
   if (!P->kern32 && K <= TT) {                                                                               \
     P->kern32 = shift == 12 ? kset_chain32_kernel<CostT, TT, (MB > 4 ? 4 : MB), 12>                          \
                             : kset_chain32_kernel<CostT, TT, (MB > 4 ? 4 : MB), 0>;                          \
+    P->kern32_lo = shift == 12 ? kset_chain32_kernel<CostT, TT, (MB > 4 ? 4 : MB) - (MB >= 4 ? 1 : 0), 12>   \
+                               : kset_chain32_kernel<CostT, TT, (MB > 4 ? 4 : MB) - (MB >= 4 ? 1 : 0), 0>;   \
+    P->minb = MB > 4 ? 4 : MB;                                                                               \
     P->kern64 = kset_chain_kernel<CostT, TT, 1>;                                                             \
     P->kernf64 = kset_chainf64_kernel<CostT, TT, 1>;                                                         \
     P->T = TT;                                                                                               \
@@ -1143,6 +1148,7 @@ static int make_plan(int H, int W, int K, int tpsi, int shift, size_t workspace_
       P->smem64 + 1024 + 9216 > (size_t)227 * 1024)
     return FLOWB200_EUNSUPPORTED;
   FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fixed32 + ((size_t)P->slot_bytes << P->slot_shift))));
+  FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern32_lo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fixed32 + ((size_t)P->slot_bytes << P->slot_shift))));
   FB_CUDA_CHECK(cudaFuncSetAttribute(P->kern64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem64));
   FB_CUDA_CHECK(cudaFuncSetAttribute(P->kernf64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem64));
   return FLOWB200_OK;
@@ -1214,7 +1220,9 @@ int ksets_phase(const int32_t* pvec, const CostT* cost, const int32_t* nprop, in
     FB_LAUNCH_CHECK();
     return FLOWB200_OK;
   }
-  P.kern32<<<c1 - c0, P.T, P.smem32[phase & 1], stream>>>(a);
+  // (1300: static shared memory + the driver's 1 KB per CTA)
+  const bool fits = (size_t)P.minb * (P.smem32[phase & 1] + 1300) <= (size_t)227 * 1024;
+  (fits ? P.kern32 : P.kern32_lo)<<<c1 - c0, P.T, P.smem32[phase & 1], stream>>>(a);
   FB_LAUNCH_CHECK();
   P.kern64<<<c1 - c0, P.T, P.smem64, stream>>>(a);   // blocks of certified chains return at once
   FB_LAUNCH_CHECK();
