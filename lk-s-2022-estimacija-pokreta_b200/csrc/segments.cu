@@ -78,11 +78,12 @@ __global__ void seg_flatten_kernel(int n, int32_t* parent, int32_t* __restrict__
   atomicAdd(&size[r], 1);
 }
 
-// FLOWB200_SEG_PREFILTER=1: settle the seed events that cannot have an effect before the replay (segments_core.cuh).
-// Off by default: checked on the host (tests/test_segments_host.py) but not yet run or timed on a GPU.
+// Settle the seed events that cannot have an effect before the replay (segments_core.cuh): on by default (8.4 instead
+// of 29.7 ms on the bench workload's checked field, same valid flags: profiles/r02_segments_prefilter{0,1}.json);
+// FLOWB200_SEG_PREFILTER=0 switches it off.
 bool seg_prefilter_enabled() {
   const char* e = getenv("FLOWB200_SEG_PREFILTER");
-  return e && e[0] == '1';
+  return !(e && e[0] == '0');
 }
 
 __global__ void seg_prefilter_invalid_kernel(SegState S) {
