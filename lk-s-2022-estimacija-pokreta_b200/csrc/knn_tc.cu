@@ -70,6 +70,7 @@ constexpr float kPadNorm = 60000.0f;   // n_hi of padding target rows: their sco
 struct KnnTcGeom {
   int H, W, cellw, cellh, ncellx, ncelly, R, K, T, Tpad, stride_s, tiles_x, tiles_y, nblk;
   int cx0, cx1;   // target cell columns searched (flowb200_params.cell_x0 / cell_x1; all: 0, ncellx)
+  uint32_t rcp_T, rcp_cellw;   // floor(2^32 / T), floor(2^32 / cellw): divisions by multiply-high + one fix-up step
   float tphi;
 };
 
@@ -470,8 +471,20 @@ __device__ __forceinline__ double exact_dist(const float* __restrict__ q, const 
 
 // candidate array entry -> target index inside the cell: the two-pass selection stores the POSITION in the cell's
 // permuted target order (the modulo is cheaper here, one lane per candidate, than in the selection's hit loop)
+// x / d and x % d for a divisor known on the host: q = mulhi(x, floor(2^32 / d)) is short of the quotient by at
+// most one for every 32-bit x
+__device__ __forceinline__ uint32_t divmod_rcp(uint32_t x, uint32_t d, uint32_t rcp, uint32_t& rem) {
+  uint32_t q = __umulhi(x, rcp);
+  uint32_t r = x - q * d;
+  if (r >= d) { ++q; r -= d; }
+  rem = r;
+  return q;
+}
+
 __device__ __forceinline__ int cand_index(const KnnTcGeom& g, uint32_t c) {
-  return (int)((c * (uint32_t)g.stride_s) % (uint32_t)g.T);
+  uint32_t rem;
+  divmod_rcp(c * (uint32_t)g.stride_s, (uint32_t)g.T, g.rcp_T, rem);
+  return (int)rem;
 }
 
 template <int KC>
@@ -496,21 +509,63 @@ __device__ __forceinline__ void emit_proposal(const KnnTcGeom& g, const float* _
 //        70 * 2^-24 = 4.2e-6 of the real-valued distance (and the float64 oracle value within 1e-14 of it);
 //   cost the float32 L1 data cost sum |fl(q-t)| in numpy's pairwise order (daisy i flann.py:178-180), exactly as
 //        sum68_numpy_order evaluates it.
+// Every lane reads a DIFFERENT target row, and the L1 data pipe serves such a request one 32-byte sector per lane
+// and pass: with 16-byte loads the kernel ran at 98 % of that pipe (17 passes per row).  The row is therefore read as
+// its nine 32-byte sectors with 256-bit loads (sm_100).  Rows are 272 bytes apart, so every other row starts in the
+// middle of a sector: the lane then works on the 72-float window that starts 4 floats before the row.  Window
+// position k is dimension k - 4*odd, and k & 7 is a compile-time register index: accumulator r[k & 7] collects the
+// dimensions numpy's r[(k - 4*odd) & 7] does, in the same order, and the final ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))
+// only exchanges its two halves (a commutative add).  Masked positions add +0, which changes no partial sum.
+__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+      : "l"(p));
+}
+
 __device__ __forceinline__ void screen_and_cost(const float* __restrict__ q, const float* __restrict__ t, float& ds,
                                                 float& cost) {
+  const bool odd = (reinterpret_cast<uintptr_t>(t) & 16) != 0;
+  const float* tb = t - (odd ? 4 : 0);          // 32-byte aligned
+  const float* qb = q - (odd ? 4 : 0);          // same window over the query row (only its in-row part is read)
   float acc = 0.f, r[8], tail[4];
 #pragma unroll
-  for (int d = 0; d < kDescDim; d += 4) {
-    const float4 a = *reinterpret_cast<const float4*>(q + d);     // same 272 B for the whole half-warp: L1 hits
-    const float4 b = *reinterpret_cast<const float4*>(t + d);
-    const float e[4] = {__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z), __fsub_rn(a.w, b.w)};
+  for (int j = 0; j < 8; ++j) r[j] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      acc = fmaf(e[i], e[i], acc);
-      const float ae = fabsf(e[i]);
-      if (d + i < 8) r[d + i] = ae;
-      else if (d + i < 64) r[(d + i) & 7] = __fadd_rn(r[(d + i) & 7], ae);
-      else tail[d + i - 64] = ae;
+  for (int i = 0; i < 8; ++i) {
+    float w[8];
+    ldg256(tb + 8 * i, w);
+    const float4 a0 = *reinterpret_cast<const float4*>(i == 0 ? q : qb + 8 * i);   // (i = 0, odd: masked below)
+    const float4 a1 = *reinterpret_cast<const float4*>(qb + 8 * i + 4);
+    float e[8] = {__fsub_rn(a0.x, w[0]), __fsub_rn(a0.y, w[1]), __fsub_rn(a0.z, w[2]), __fsub_rn(a0.w, w[3]),
+                  __fsub_rn(a1.x, w[4]), __fsub_rn(a1.y, w[5]), __fsub_rn(a1.z, w[6]), __fsub_rn(a1.w, w[7])};
+    if (i == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) e[j] = odd ? 0.f : e[j];   // the four floats in front of an odd row
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc = fmaf(e[j], e[j], acc);
+      r[j] = __fadd_rn(r[j], fabsf(e[j]));
+    }
+  }
+  // last sector: window positions 64..67 (dimensions 64..67 of an even row, 60..63 of an odd one) and, for odd rows
+  // only, 68..71 (their dimensions 64..67); an even row's second half belongs to the next pixel and is not read
+  {
+    const float4 x = *reinterpret_cast<const float4*>(tb + 64);
+    const float4 a = *reinterpret_cast<const float4*>(qb + 64);
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f), b = y;
+    if (odd) {
+      y = *reinterpret_cast<const float4*>(tb + 68);
+      b = *reinterpret_cast<const float4*>(qb + 68);
+    }
+    const float ex[4] = {__fsub_rn(a.x, x.x), __fsub_rn(a.y, x.y), __fsub_rn(a.z, x.z), __fsub_rn(a.w, x.w)};
+    const float ey[4] = {__fsub_rn(b.x, y.x), __fsub_rn(b.y, y.y), __fsub_rn(b.z, y.z), __fsub_rn(b.w, y.w)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc = fmaf(ex[j], ex[j], acc);
+      acc = fmaf(ey[j], ey[j], acc);
+      r[j] = __fadd_rn(r[j], odd ? fabsf(ex[j]) : 0.f);
+      tail[j] = odd ? fabsf(ey[j]) : fabsf(ex[j]);
     }
   }
   float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
@@ -572,15 +627,17 @@ knn_rerank_kernel(const float* __restrict__ desc_src, const float* __restrict__ 
       const float* tp1 = nullptr;
       if (sub < n) {
         id0 = cand_index(g, cand[task * kCand + sub]);
-        const int r = id0 / g.cellw, cc = id0 - r * g.cellw;
-        tp0 = desc_tgt + ((size_t)(ty0 + r) * g.W + tx0 + cc) * kDescDim;
+        uint32_t cc;
+        const int r = (int)divmod_rcp((uint32_t)id0, (uint32_t)g.cellw, g.rcp_cellw, cc);
+        tp0 = desc_tgt + ((size_t)(ty0 + r) * g.W + tx0 + (int)cc) * kDescDim;
         screen_and_cost(qp, tp0, ds0, co0);
       }
       const bool two = n > 16;
       if (two && 16 + sub < n) {
         id1 = cand_index(g, cand[task * kCand + 16 + sub]);
-        const int r = id1 / g.cellw, cc = id1 - r * g.cellw;
-        tp1 = desc_tgt + ((size_t)(ty0 + r) * g.W + tx0 + cc) * kDescDim;
+        uint32_t cc;
+        const int r = (int)divmod_rcp((uint32_t)id1, (uint32_t)g.cellw, g.rcp_cellw, cc);
+        tp1 = desc_tgt + ((size_t)(ty0 + r) * g.W + tx0 + (int)cc) * kDescDim;
         screen_and_cost(qp, tp1, ds1, co1);
       }
       // rank by the screening distance; note every pair it cannot order with certainty
@@ -633,8 +690,9 @@ knn_rerank_kernel(const float* __restrict__ desc_src, const float* __restrict__ 
       }
       const size_t obase = pix * g.K + (size_t)KC * blk;
       if (sub < n && rank0 < KC) {
-        const int r = id0 / g.cellw, cc = id0 - r * g.cellw;
-        pvec[obase + rank0] = pack_vec(ty0 + r - qy, tx0 + cc - qx);
+        uint32_t cc;
+        const int r = (int)divmod_rcp((uint32_t)id0, (uint32_t)g.cellw, g.rcp_cellw, cc);
+        pvec[obase + rank0] = pack_vec(ty0 + r - qy, tx0 + (int)cc - qx);
         const float cc0 = co0 < g.tphi ? co0 : g.tphi;            // min(tphi, sum) (:178-180)
         lcost[obase + rank0] = cc0;
         const unsigned long long k0 = ((unsigned long long)__float_as_uint(cc0) << 32) | (uint32_t)(KC * blk + rank0);
@@ -642,8 +700,9 @@ knn_rerank_kernel(const float* __restrict__ desc_src, const float* __restrict__ 
         if (knn_idx) knn_idx[(pix * g.nblk + blk) * KC + rank0] = id0;
       }
       if (two && 16 + sub < n && rank1 < KC) {
-        const int r = id1 / g.cellw, cc = id1 - r * g.cellw;
-        pvec[obase + rank1] = pack_vec(ty0 + r - qy, tx0 + cc - qx);
+        uint32_t cc;
+        const int r = (int)divmod_rcp((uint32_t)id1, (uint32_t)g.cellw, g.rcp_cellw, cc);
+        pvec[obase + rank1] = pack_vec(ty0 + r - qy, tx0 + (int)cc - qx);
         const float cc1 = co1 < g.tphi ? co1 : g.tphi;
         lcost[obase + rank1] = cc1;
         const unsigned long long k1 = ((unsigned long long)__float_as_uint(cc1) << 32) | (uint32_t)(KC * blk + rank1);
@@ -784,6 +843,8 @@ static KnnTcGeom make_tc_geom(const flowb200_params* p) {
   if (s < 1) s = 1;
   while (gcd_i(s, g.T) != 1) ++s;
   g.stride_s = s;
+  g.rcp_T = g.T > 1 ? (uint32_t)((1ull << 32) / (uint64_t)g.T) : 0xffffffffu;
+  g.rcp_cellw = g.cellw > 1 ? (uint32_t)((1ull << 32) / (uint64_t)g.cellw) : 0xffffffffu;
   const int r = 2 * g.R + 1;
   g.tiles_x = (min(g.W, r * g.cellw) + kTileW * kTilesPerItem - 1) / (kTileW * kTilesPerItem);
   g.tiles_y = (min(g.H, r * g.cellh) + kTileH - 1) / kTileH;
