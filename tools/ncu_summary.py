@@ -12,7 +12,10 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_tensor.sum", "smsp__warps_eligible.avg.per_cycle_active"]
+        "sm__inst_executed_pipe_tensor.sum", "smsp__warps_eligible.avg.per_cycle_active",
+        "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 ix = {h: i for i, h in enumerate(hdr)}
 launches = []
 for r in rows[2:]:
