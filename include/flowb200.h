@@ -162,6 +162,16 @@ int flowb200_bcd_phase(const int32_t* pvec, const void* cost, const int32_t* npr
 int flowb200_best_labels(const float* lcost, const int32_t* nprop, int H, int W, int K, int32_t* labels,
                          flowb200_stream_t stream);
 
+/* Single-huge-image mode: slot ranges of proposal arrays <-> a flat exchange buffer, one launch for a whole copy plan
+ * (huge.py copy_plan; the reference has no multi-GPU path, this replaces per-range strided copies).  table: n_entries
+ * (at most 65535) x 8 int64 {y0, y1, x0, x1, slot0, n, off_vec, off_cost}, x relative to the array; for y0 <= y < y1,
+ * x0 <= x < x1, 0 <= s < n, with i = (y - y0) * (x1 - x0) + (x - x0):
+ *   flat[off_vec + i * n + s]  <->  vec [(y * width + x) * K + slot0 + s]
+ *   flat[off_cost + i * n + s] <->  cost[(y * width + x) * K + slot0 + s]   (bit pattern of the float)
+ * to_flat != 0 packs the arrays into flat, 0 unpacks flat into the arrays.  Ranges must lie inside the arrays. */
+int flowb200_slot_copy(const int64_t* table, int n_entries, int32_t* vec, float* cost, int width, int K,
+                       int32_t* flat, int to_flat, flowb200_stream_t stream);
+
 /* ---- A5  vratiKonacniFlow (daisy i flann.py:192-197) + A12 FlowImage.ucitajFlow (postprocessing.py:7-17) ----
  * flow_yx (optional): float64 [H][W][2] = (dy,dx);  uvv (optional): float32 [H][W][3] = (dx, dy, 1). */
 int flowb200_flow_from_labels(const int32_t* pvec, const int32_t* labels, int H, int W, int K,

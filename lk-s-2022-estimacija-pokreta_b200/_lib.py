@@ -55,6 +55,7 @@ SYMBOLS = {
     "flowb200_bcd_phase": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "flowb200_best_labels": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "flowb200_slot_copy": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P]),
     "flowb200_flow_from_labels": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "flowb200_consistency": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "flowb200_segments_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),

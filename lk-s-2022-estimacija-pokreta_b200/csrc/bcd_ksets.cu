@@ -52,13 +52,26 @@ __device__ __forceinline__ int32_t quant_cost(CostT c, double lamda, int shift) 
 constexpr int kSortWarps = 8;
 constexpr int kCntSize = kHashSize + kHashSize / 32;   // 1056, a multiple of 4
 
+// single-huge-image mode: line (column x or row y) `line` of `nlines` belongs to chain line >> 1 of its parity's
+// phase; part `part` of `nparts` runs a contiguous share of every phase's chains (owned_chains on the host)
+__device__ __forceinline__ bool owns_line(int line, int nlines, int part, int nparts) {
+  const long long nch = (line & 1) ? nlines / 2 : (nlines + 1) / 2;
+  const int c = line >> 1;
+  return c >= (int)(nch * part / nparts) && c < (int)(nch * (part + 1) / nparts);
+}
+
 __global__ void __launch_bounds__(kSortWarps * 32)
 kset_sort_kernel(const int32_t* __restrict__ pvec, const int32_t* __restrict__ nprop, int npix, int K, int Kst,
-                 int bshift, uint16_t* __restrict__ sorig, int32_t* __restrict__ svec) {
+                 int bshift, uint16_t* __restrict__ sorig, int32_t* __restrict__ svec, int H, int W, int part,
+                 int nparts) {
   __shared__ __align__(16) int cnt_s[kSortWarps][kCntSize];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* cnt = cnt_s[warp];
   for (int pix = blockIdx.x * kSortWarps + warp; pix < npix; pix += gridDim.x * kSortWarps) {
+    if (nparts > 1) {   // only pixels on a column or row chain this part runs (their records are the ones built)
+      const int y = pix / W, x = pix - y * W;
+      if (!owns_line(x, W, part, nparts) && !owns_line(y, H, part, nparts)) continue;
+    }
     const int n = nprop[pix];
     const int32_t* v = pvec + (size_t)pix * K;
     uint16_t* o = sorig + (size_t)pix * Kst;
@@ -202,10 +215,7 @@ kset_build_kernel(const int32_t* __restrict__ pvec, const CostT* __restrict__ co
     const int p = task - orient * npix;
     const int y = p / W, x = p - y * W;
     if (nparts > 1) {   // only the records of the chains this part runs (column x: chain x/2 of phase 0 or 2; row y alike)
-      const int line = orient ? y : x;
-      const long long nch = orient ? ((line & 1) ? H / 2 : (H + 1) / 2) : ((line & 1) ? W / 2 : (W + 1) / 2);
-      const int c = line >> 1;
-      if (c < (int)(nch * part / nparts) || c >= (int)(nch * (part + 1) / nparts)) {
+      if (!owns_line(orient ? y : x, orient ? H : W, part, nparts)) {
         if (t == 0) desc[task] = 0ull;
         continue;
       }
@@ -1171,7 +1181,7 @@ int ksets_prepare(const int32_t* pvec, const CostT* cost, const int32_t* nprop, 
   FB_CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), stream));
   int32_t* svec = reinterpret_cast<int32_t*>(ws + L.svec);
   kset_sort_kernel<<<min((npix + kSortWarps - 1) / kSortWarps, 8 * kNumSMs), kSortWarps * 32, 0, stream>>>(
-      pvec, nprop, npix, K, L.Kst, P.bshift, sorig, svec);
+      pvec, nprop, npix, K, L.Kst, P.bshift, sorig, svec, H, W, part, nparts);
   FB_LAUNCH_CHECK();
   const size_t bsmem = build_smem_bytes(L.Kpad);
   auto bk = kset_build_kernel<CostT>;

@@ -131,6 +131,44 @@ extern "C" int flowb200_best_labels(const float* lcost, const int32_t* nprop, in
   return FLOWB200_OK;
 }
 
+// Slot-range copies of the single-huge-image merge (huge.py: pack_band / unpack_band as ONE launch instead of one
+// strided copy per range).  blockIdx.y = table entry, one warp per pixel of the entry, lanes over the slots: both
+// sides of the copy are contiguous runs of n slots.
+__global__ void slot_copy_kernel(const long long* __restrict__ table, int32_t* __restrict__ vec,
+                                 int32_t* __restrict__ cost, int width, int K, int32_t* __restrict__ flat, int to_flat) {
+  const long long* e = table + 8 * (size_t)blockIdx.y;
+  const int y0 = (int)e[0], y1 = (int)e[1], x0 = (int)e[2], x1 = (int)e[3], slot0 = (int)e[4], n = (int)e[5];
+  const long long off_vec = e[6], off_cost = e[7];
+  const int cols = x1 - x0, npix = (y1 - y0) * cols;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < npix; i += gridDim.x * wpb) {
+    const int r = i / cols, c = i - r * cols;
+    const size_t a = ((size_t)(y0 + r) * width + (x0 + c)) * K + slot0;
+    const size_t f = (size_t)i * n;
+    for (int s = lane; s < n; s += 32) {
+      if (to_flat) {
+        flat[off_vec + f + s] = vec[a + s];
+        flat[off_cost + f + s] = cost[a + s];
+      } else {
+        vec[a + s] = flat[off_vec + f + s];
+        cost[a + s] = flat[off_cost + f + s];
+      }
+    }
+  }
+}
+
+extern "C" int flowb200_slot_copy(const int64_t* table, int n_entries, int32_t* vec, float* cost, int width, int K,
+                                  int32_t* flat, int to_flat, flowb200_stream_t stream) {
+  if (n_entries < 0 || width <= 0 || K <= 0) return FLOWB200_EINVAL;
+  if (n_entries == 0) return FLOWB200_OK;
+  if (!table || !vec || !cost || !flat || n_entries > 65535) return FLOWB200_EINVAL;
+  static_assert(sizeof(long long) == sizeof(int64_t), "table entries are 64-bit");
+  slot_copy_kernel<<<dim3(64, (unsigned)n_entries), 256, 0, stream>>>(
+      reinterpret_cast<const long long*>(table), vec, reinterpret_cast<int32_t*>(cost), width, K, flat, to_flat);
+  FB_LAUNCH_CHECK();
+  return FLOWB200_OK;
+}
+
 extern "C" int flowb200_flow_from_labels(const int32_t* pvec, const int32_t* labels, int H, int W, int K,
                                          double* flow_yx, float* uvv, flowb200_stream_t stream) {
   if (!pvec || !labels || H <= 0 || W <= 0 || K <= 0) return FLOWB200_EINVAL;

@@ -15,6 +15,7 @@ consistency check are cheap and run replicated, with identical results on every 
 All functions here are host-side planning and torch.distributed plumbing; the arithmetic is the C-ABI kernels'.
 """
 from dataclasses import dataclass
+from functools import lru_cache
 
 import numpy as np
 
@@ -36,8 +37,11 @@ class Band:
         return self.sx1 - self.sx0
 
 
+@lru_cache(maxsize=64)
 def band_plan(p: FlowParams, world: int):
-    """Contiguous, balanced bands of target cell columns.  Ranks beyond the number of cell columns get empty bands."""
+    """Contiguous, balanced bands of target cell columns.  Ranks beyond the number of cell columns get empty bands.
+    (The plans of this module are pure functions of the frozen parameters and are cached: at 3840x2160 they cost the
+    host more per call than the device needs for the copies they describe.)"""
     n, R, cw = p.ncellx, p.cell_radius, p.cellw
     bands = []
     for r in range(world):
@@ -60,6 +64,7 @@ def sub_params(p: FlowParams, b: Band) -> FlowParams:
     return replace(p.with_shape(p.H, b.width), cell_x0=c0, cell_x1=c0 + (b.ci_hi - b.ci_lo))
 
 
+@lru_cache(maxsize=64)
 def _row_groups(p: FlowParams):
     """Maximal runs of image rows whose number of cell rows in range is the same: [(y0, y1, n_cj)]."""
     out = []
@@ -76,6 +81,7 @@ def _row_groups(p: FlowParams):
     return out
 
 
+@lru_cache(maxsize=256)
 def copy_plan(p: FlowParams, b: Band):
     """Slot-range copies that place band `b`'s proposals into the full-image arrays:
     [(y0, y1, x0, x1, dst_slot0, src_slot0, nslots)] with dst[y0:y1, x0:x1, dst_slot0:+n] = src[y0:y1, x0-sx0:x1-sx0,
@@ -111,6 +117,17 @@ def nn_counts(p: FlowParams):
     nx = np.maximum(0, np.minimum(p.ncellx - 1, qx + R) - np.maximum(0, qx - R) + 1)
     ny = np.maximum(0, np.minimum(p.ncelly - 1, qy + R) - np.maximum(0, qy - R) + 1)
     return (p.k_cell * ny[:, None] * nx[None, :]).astype(np.int32)
+
+
+def nn_counts_on(p: FlowParams, device):
+    """nn_counts evaluated on `device` with torch (no host pass over the image, no host-to-device copy)."""
+    import torch
+    R = p.cell_radius
+    qx = torch.arange(p.W, device=device, dtype=torch.int32) // p.cellw
+    qy = torch.arange(p.H, device=device, dtype=torch.int32) // p.cellh
+    nx = ((qx + R).clamp(max=p.ncellx - 1) - (qx - R).clamp(min=0) + 1).clamp(min=0)
+    ny = ((qy + R).clamp(max=p.ncelly - 1) - (qy - R).clamp(min=0) + 1).clamp(min=0)
+    return (p.k_cell * ny[:, None] * nx[None, :]).to(torch.int32)
 
 
 def _plan_elems(plan):
@@ -159,9 +176,42 @@ def _best_labels(lcost, nprop):
     return torch.where(nprop > 0, labels, torch.zeros_like(labels))
 
 
+_TABLES = {}
+
+
+def _plan_table(p: FlowParams, world: int, which, cap: int, device):
+    """The copy plans as the int64 table flowb200_slot_copy takes, on `device` (cached).  which = rank: that band's
+    pack table (array = the rank's sub-image, flat = its send buffer); which = -1: the unpack table of ALL bands
+    (array = the full image, flat = the all-gather result, band r at offset r * cap)."""
+    import torch
+    key = (p, world, which, cap, str(device))
+    t = _TABLES.get(key)
+    if t is None:
+        rows = []
+        for b in band_plan(p, world):
+            if which >= 0 and b.rank != which:
+                continue
+            plan = copy_plan(p, b)
+            half = _plan_elems(plan)
+            o = 0
+            for y0, y1, x0, x1, d0, s0, n in plan:
+                if which >= 0:
+                    rows.append((y0, y1, x0 - b.sx0, x1 - b.sx0, s0, n, o, half + o))
+                else:
+                    rows.append((y0, y1, x0, x1, d0, n, b.rank * cap + o, b.rank * cap + half + o))
+                o += (y1 - y0) * (x1 - x0) * n
+        t = torch.tensor(rows, dtype=torch.int64).reshape(-1, 8).to(device)
+        if len(_TABLES) > 64:
+            _TABLES.clear()
+        _TABLES[key] = t
+    return t
+
+
 def merge_bands(p: FlowParams, bands, rank, sub_pvec, sub_lcost, device, dist=None, blocks=None):
     """Every rank contributes the slot ranges of its band (packed, no halo columns, no unused slots) to ONE all-gather;
-    every rank unpacks all bands into the full proposal set.
+    every rank unpacks all bands into the full proposal set.  On the device packing and unpacking are one
+    flowb200_slot_copy launch each; CPU tensors (the gloo tests of this module) take the torch slicing of
+    pack_band / unpack_band, which defines what the kernel does.
 
     sub_pvec int32 / sub_lcost float32: (H, band width, K) of THIS rank (None for an empty band).
     blocks (tests): {rank: (pvec, lcost)} of the other ranks, packed and unpacked locally instead of the all-gather.
@@ -174,26 +224,39 @@ def merge_bands(p: FlowParams, bands, rank, sub_pvec, sub_lcost, device, dist=No
     sizes = [2 * _plan_elems(copy_plan(p, b)) for b in bands]
     cap = max(max(sizes), 1)
     world = len(bands)
-    send = torch.empty(cap, dtype=torch.int32, device=device)
-    if sizes[rank]:
-        pack_band(p, bands[rank], sub_pvec, sub_lcost, send)
+    on_gpu = pvec.is_cuda
+    if on_gpu:
+        from . import ops
+
+    def pack(b, pv, lc, out):
+        if on_gpu:
+            ops.slot_copy(_plan_table(p, world, b.rank, cap, device), pv, lc, out, True)
+        else:
+            pack_band(p, b, pv, lc, out)
+
+    recv = torch.empty((world, cap), dtype=torch.int32, device=device)
     if blocks is not None or dist is None or world == 1:
-        recv = torch.empty((world, cap), dtype=torch.int32, device=device)
-        recv[rank] = send
+        if sizes[rank]:
+            pack(bands[rank], sub_pvec, sub_lcost, recv[rank])
         if blocks is not None:
             for b in bands:
                 if b.rank != rank and sizes[b.rank]:
-                    pack_band(p, b, blocks[b.rank][0], blocks[b.rank][1], recv[b.rank])
+                    pack(b, blocks[b.rank][0], blocks[b.rank][1], recv[b.rank])
     else:
-        recv = torch.empty((world, cap), dtype=torch.int32, device=device)
+        send = torch.empty(cap, dtype=torch.int32, device=device)
+        if sizes[rank]:
+            pack(bands[rank], sub_pvec, sub_lcost, send)
         try:
             dist.all_gather_into_tensor(recv.view(-1), send)
         except (RuntimeError, AttributeError, NotImplementedError):
             dist.all_gather([recv[r] for r in range(world)], send)
-    for b in bands:
-        if sizes[b.rank]:
-            unpack_band(p, b, recv[b.rank], pvec, lcost)
-    nprop = torch.from_numpy(nn_counts(p)).to(device)
+    if on_gpu:
+        ops.slot_copy(_plan_table(p, world, -1, cap, device), pvec, lcost, recv.view(-1), False)
+    else:
+        for b in bands:
+            if sizes[b.rank]:
+                unpack_band(p, b, recv[b.rank], pvec, lcost)
+    nprop = nn_counts_on(p, device)
     labels = _best_labels(lcost, nprop)       # first strict argmin of the data costs (daisy i flann.py:181-184)
     return pvec, lcost, nprop, labels
 

@@ -185,6 +185,17 @@ def best_labels(lcost, nprop):
     return labels
 
 
+def slot_copy(table, vec, cost, flat, to_flat):
+    """flowb200_slot_copy: the slot ranges listed in `table` (int64 (n, 8), see include/flowb200.h) between the proposal
+    arrays vec int32 / cost float32 (rows, width, K) and the flat int32 buffer; to_flat packs, otherwise unpacks."""
+    lib = _lib.load()
+    _, width, K = vec.shape
+    assert cost.shape == vec.shape and table.dim() == 2 and table.shape[1] == 8
+    _lib.check(lib.flowb200_slot_copy(_ptr(table, torch.int64, "table"), int(table.shape[0]), _ptr(vec, torch.int32, "vec"),
+                                      _ptr(cost, torch.float32, "cost"), width, K, _ptr(flat, torch.int32, "flat"),
+                                      1 if to_flat else 0, _stream()), "flowb200_slot_copy")
+
+
 def flow_from_labels(pvec, labels, want_yx=True, want_uvv=True):
     """vratiKonacniFlow (+ FlowImage layout).  Returns (flow_yx float64 (H,W,2) | None, uvv float32 (H,W,3) | None)."""
     lib = _lib.load()

@@ -474,6 +474,29 @@ def test_banded_search_on_device_merges_to_full(world):
             assert torch.equal(g, w)
 
 
+@pytest.mark.parametrize("world", [2, 5])
+def test_slot_copy_kernel_equals_the_torch_slicing(world):
+    """flowb200_slot_copy (one launch per pack / unpack) against pack_band / unpack_band evaluated with torch on the
+    CPU, on random band blocks: merged proposals, costs, nprop and bestlabels bit-identical on every rank."""
+    huge, params = pkg("huge"), pkg("params")
+    H, W = 110, 657          # 9 cell columns, ragged cell rows (110 = 4 * 25 + 10)
+    p = params.for_k(150, H=H, W=W, knn_mode=1)
+    rng = np.random.default_rng(world)
+    bands = huge.band_plan(p, world)
+    cpu = {}
+    for bd in bands:
+        if bd.ci_hi > bd.ci_lo:
+            pv = torch.from_numpy(rng.integers(-2 ** 31, 2 ** 31 - 1, (H, bd.width, p.maxnprop), dtype=np.int64).astype(np.int32))
+            lc = torch.from_numpy(rng.random((H, bd.width, p.maxnprop), dtype=np.float32) * 3)
+            cpu[bd.rank] = (pv, lc)
+    gpu = {r: (a.cuda(), b.cuda()) for r, (a, b) in cpu.items()}
+    for rank in range(world):
+        want = huge.merge_bands(p, bands, rank, *cpu.get(rank, (None, None)), "cpu", blocks=cpu)
+        got = huge.merge_bands(p, bands, rank, *gpu.get(rank, (None, None)), torch.device("cuda"), blocks=gpu)
+        for g, w in zip(got, want):
+            assert torch.equal(g.cpu(), w)
+
+
 def test_two_ranks_nccl_flow_pair_equals_one_gpu(tmp_path):
     """torchrun, 2 ranks over NCCL: the sharded pair pipeline returns, on both ranks, exactly what one GPU computes."""
     if torch.cuda.device_count() < 2:

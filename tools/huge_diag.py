@@ -30,7 +30,8 @@ for rep in range(2):
     sub = timed("search (own band)", lambda: ops.knn_proposals(d0[:, bd.sx0:bd.sx1].contiguous(), d1[:, bd.tx0:bd.tx1].contiguous(), huge.sub_params(p, bd))[:2])
     pv, lc, npr, lab = timed("merge (broadcast + copies + argmin)", lambda: huge.merge_bands(p, bands, rank, sub[0], sub[1], d0.device, D))
     timed("random proposals", lambda: ops.random_proposals(d0, d1, p, pv, lc, npr, lab, seed=1))
-    ws = ops.bcd_workspace(pv)
+    del sub
+    ws = ops.bcd_workspace(pv, world)
     kw = dict(mode=lib.BCD_INT32_F32COST, lamda=p.lamda, tpsi=p.tpsi, cost_shift=p.cost_shift)
     timed("bcd prepare (own chains)", lambda: ops.bcd_prepare(pv, lc, npr, ws, rank, world, **kw))
     for sweep in range(4):
