@@ -56,6 +56,52 @@ def test_banded_search_merges_to_full(H, W, cw, ch, R, k, world):
         assert np.array_equal(labels.numpy(), want[3])
 
 
+def _slot_copy_emul(table, vec, cost, flat, to_flat):
+    """What include/flowb200.h says flowb200_slot_copy does, in numpy (cost as its int32 bit pattern)."""
+    ci = cost.view(np.int32)
+    for y0, y1, x0, x1, slot0, n, off_vec, off_cost in table:
+        cnt = (y1 - y0) * (x1 - x0) * n
+        if to_flat:
+            flat[off_vec:off_vec + cnt] = vec[y0:y1, x0:x1, slot0:slot0 + n].reshape(-1)
+            flat[off_cost:off_cost + cnt] = ci[y0:y1, x0:x1, slot0:slot0 + n].reshape(-1)
+        else:
+            vec[y0:y1, x0:x1, slot0:slot0 + n] = flat[off_vec:off_vec + cnt].reshape(y1 - y0, x1 - x0, n)
+            ci[y0:y1, x0:x1, slot0:slot0 + n] = flat[off_cost:off_cost + cnt].reshape(y1 - y0, x1 - x0, n)
+
+
+@pytest.mark.parametrize("H,W,cw,ch,R,k,world", [(40, 70, 8, 6, 2, 3, 3), (33, 95, 9, 7, 1, 2, 4), (30, 26, 8, 6, 2, 2, 8)])
+def test_slot_copy_tables_describe_the_same_copies_as_the_torch_slicing(H, W, cw, ch, R, k, world):
+    """The int64 tables handed to flowb200_slot_copy on the device (huge._plan_table), applied with the header's
+    definition of the kernel, give what pack_band / unpack_band (the CPU path of merge_bands) give."""
+    import torch
+    params, huge = pkg("params"), pkg("huge")
+    r = 2 * R + 1
+    p = params.FlowParams(H=H, W=W, cellw=cw, cellh=ch, cell_radius=R, k_cell=k, n_gauss=0, maxnprop=r * r * k + 3)
+    rng = np.random.default_rng(world)
+    bands = huge.band_plan(p, world)
+    sizes = [2 * huge._plan_elems(huge.copy_plan(p, b)) for b in bands]
+    cap = max(max(sizes), 1)
+    K = p.maxnprop
+    blocks = {b.rank: (rng.integers(-9, 9, (H, b.width, K)).astype(np.int32), rng.random((H, b.width, K), dtype=np.float32))
+              for b in bands if b.ci_hi > b.ci_lo}
+    recv = np.zeros(world * cap, dtype=np.int32)
+    for b in bands:
+        if sizes[b.rank]:
+            t = huge._plan_table(p, world, b.rank, cap, "cpu").numpy()
+            send = np.zeros(cap, dtype=np.int32)
+            _slot_copy_emul(t, blocks[b.rank][0], blocks[b.rank][1], send, True)
+            want = torch.zeros(cap, dtype=torch.int32)
+            huge.pack_band(p, b, torch.from_numpy(blocks[b.rank][0]), torch.from_numpy(blocks[b.rank][1]), want)
+            assert np.array_equal(send, want.numpy())
+            recv[b.rank * cap:(b.rank + 1) * cap] = send
+    pvec, lcost = np.full((H, W, K), -1, dtype=np.int32), np.full((H, W, K), 1000.0, dtype=np.float32)
+    _slot_copy_emul(huge._plan_table(p, world, -1, cap, "cpu").numpy(), pvec, lcost, recv, False)
+    tb = {r_: (torch.from_numpy(a), torch.from_numpy(c)) for r_, (a, c) in blocks.items()}
+    mine = tb.get(0, (None, None))
+    want = huge.merge_bands(p, bands, 0, mine[0], mine[1], "cpu", blocks=tb)
+    assert np.array_equal(pvec, want[0].numpy()) and np.array_equal(lcost, want[1].numpy())
+
+
 def test_two_gloo_ranks_exchange_bands(tmp_path):
     pytest.importorskip("torch")
     script = tmp_path / "w.py"
