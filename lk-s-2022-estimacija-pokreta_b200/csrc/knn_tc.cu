@@ -648,7 +648,8 @@ knn_rerank_kernel(const float* __restrict__ desc_src, const float* __restrict__ 
       const int nl = n < 16 ? n : 16;   // (lanes >= n hold infinity: "certainly larger", they change nothing)
       if (!two) {   // (uniform over the half-warp) the common case: one round, candidates 0..n-1
         for (int l = 0; l < nl; ++l) {
-          const float ol = __shfl_sync(gmask, lo0, l, 16), oh = __shfl_sync(gmask, hi0, l, 16);
+          const float od = __shfl_sync(gmask, ds0, l, 16);     // (a shuffle is a pass of the L1 data pipe: send one value)
+          const float ol = od * (1.0f - 1.0e-5f), oh = od * (1.0f + 1.0e-5f);
           rank0 += oh < lo0;                                   // certainly smaller
           amb0 |= (l != sub) && !(oh < lo0) && !(hi0 < ol);    // intervals overlap
         }
